@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of the hot path (Gabor bank + k-means + BSD metrics) on synthetic
+BSDS-shaped data (481x321 RGB, 5 Voronoi ground truths per image).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port, all host cores)
+
+A step = one pass of the whole path over one batch of `--images` images per GPU (BASELINE.json
+configs[1]: a 200-image BSDS-test-shaped batch).  Weak scaling: every rank processes its own batch.
+  value  : images/s with inputs already resident in HBM (device timing, CUDA events, max over ranks)
+  e2e    : images/s through the C ABI's host entry point (pinned host buffers in, records out)
+The oracle (oracle/) is executed only for the cpu_baseline / --impl reference legs.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, G, K_CLUSTERS, ITERS = 321, 481, 5, 8, 20
+METRIC = "images/sec (481x321 RGB, Gabor+cluster+BSD eval)"
+
+
+def make_data(n, start=0, workers=None):
+    """n synthetic images + ground truths (SURVEY.md §8 d), generated in parallel on the host."""
+    from concurrent.futures import ProcessPoolExecutor
+    from gabor_color_image_segmentation_b200.synth import synth_image, synth_ground_truths
+    workers = workers or min(os.cpu_count() or 1, 16)
+    idx = list(range(start, start + n))
+    if n <= 4 or workers <= 1:
+        imgs = [synth_image(i, H, W) for i in idx]
+        gts = [synth_ground_truths(i, H, W, G) for i in idx]
+    else:
+        with ProcessPoolExecutor(workers) as ex:
+            imgs = list(ex.map(synth_image, idx, chunksize=4))
+            gts = list(ex.map(synth_ground_truths, idx, chunksize=4))
+    return np.stack(imgs), np.stack(gts)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.samples, self.stop_flag = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples), "power_w_max": max(float(s[2]) for s in self.samples)}
+
+
+def cpu_pipeline_rate(n_images, threads):
+    """Oracle port of the whole path on `threads` host threads; returns (images/s, seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as orc
+    from gabor_color_image_segmentation_b200.pipeline import init_indices_for
+    orc.lib()
+    imgs, gts = make_data(n_images, start=10_000, workers=1)   # no fork once CUDA is up
+    idx = init_indices_for(range(n_images), H * W, K_CLUSTERS)
+
+    def one(i):
+        _oracle_image(orc, imgs[i], gts[i], idx[i])
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(one, range(n_images)))
+    dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
+def _oracle_image(orc, img, gts, idx):
+    labels, _, _ = orc.segment_image(img, K_CLUSTERS, ITERS, init_idx=idx)
+    c = orc.label_counts(labels, list(gts))
+    return orc.finish_metrics(c)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    sample = max(threads, 4)
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_pipeline_rate(min(threads, 2), threads)
+    rates, secs = [], []
+    for _ in range(args.steps):
+        r, dt = cpu_pipeline_rate(sample, threads)
+        rates.append(r); secs.append(dt)
+    value = sample * len(secs) / sum(secs)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: synthetic BSDS-shaped 321x481 RGB, bank 4x6, k=8, T=20, G=5",
+                       "images_per_step": sample},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+                             "sample": "%d images per step, one image per host thread, C oracle "
+                                       "(fp64 separable Gabor + fp32-exact k-means + metrics)" % sample},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from gabor_color_image_segmentation_b200 import Plan, _lib
+    from gabor_color_image_segmentation_b200.metrics import finish_batch
+    from gabor_color_image_segmentation_b200.pipeline import SUM_KEYS, init_indices_for, reduce_sums
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this framework has no CPU path; use --impl reference for the CPU arm)")
+    B = args.images
+    # every rank gets its own images (weak scaling); generate `unique` of them and cycle.
+    # Host-side generation forks workers, so it runs before CUDA/NCCL are initialised.
+    unique = min(B, args.unique)
+    imgs_u, gts_u = make_data(unique, start=rank * 100_000, workers=max(1, min(16, (os.cpu_count() or 1) // max(world, 1))))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    reps = (B + unique - 1) // unique
+    imgs = np.concatenate([imgs_u] * reps)[:B]
+    gts = np.concatenate([gts_u] * reps)[:B]
+    idx = init_indices_for(range(rank * B, rank * B + B), H * W, K_CLUSTERS)
+
+    plan = Plan(H, W, max_batch=B, k=K_CLUSTERS, iters=ITERS, max_gt=G, n_lab_cap=64, group=args.group)
+    d_img = torch.from_numpy(imgs).to(dev)
+    d_gt = torch.from_numpy(gts.view(np.int16)).to(dev)
+    d_idx = torch.from_numpy(idx).to(dev)
+    h_img = torch.from_numpy(imgs).pin_memory()
+    h_gt = torch.from_numpy(gts.view(np.int16)).pin_memory()
+    h_idx = torch.from_numpy(idx).pin_memory()
+
+    def finish(c):
+        m = finish_batch(c)
+        local_sums = np.array([m[k].sum() for k in SUM_KEYS] + [float(len(c.bd_count))])
+        return reduce_sums(local_sums, dev)
+
+    def step_device():
+        plan.pipeline_device(d_img, d_gt, d_idx)
+        return finish(plan.fetch())
+
+    def step_host():
+        return finish(plan.pipeline_host(h_img, h_gt, h_idx, B))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        sums = step_device()
+    # ---- value: device-resident inputs, CUDA events, max over ranks ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sums = step_device()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.summary()
+    # ---- e2e: host buffers through the C ABI ----
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sums_h = step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+    else:
+        e2e_ms = e2e_s * 1e3
+    assert np.array_equal(sums, sums_h), "device-resident and host-buffer passes disagree"
+
+    # ---- per-stage device times (CUDA events inside the library) for the roofline ----
+    plan.set_profiling(True)
+    plan.pipeline_device(d_img, d_gt, d_idx)
+    plan.fetch()
+    stage = plan.last_stage_ms()
+    plan.set_profiling(False)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        N, D = H * W, 72
+        km_bytes = B * (ITERS * N * D * 4 + N * 4)                  # T*N*D*4 + N*4 per image
+        gabor_bytes = B * N * (3 + D * 4)
+        gabor_flop = B * 6.98e9                                     # SURVEY.md §8(d), complex-separable count
+        fma_peak = measure_fma_peak()
+        km_gbs = km_bytes / (stage["kmeans"] * 1e-3) / 1e9
+        gb_tfs = gabor_flop / (stage["gabor"] * 1e-3) / 1e12
+        total_imgs = B * world * args.steps
+        dominant = "kmeans" if stage["kmeans"] >= stage["gabor"] else "gabor"
+        roof_km = {"kernel": "km_pass_kernel<8> (x%d launches per group)" % ITERS, "bound": "hbm", "achieved": km_gbs,
+                   "peak": hbm_peak, "unit": "GB/s", "frac": km_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                   "ms_per_step": stage["kmeans"]}
+        roof_gb = {"kernel": "gabor_bank_kernel", "bound": "fp32", "achieved": gb_tfs,
+                   "peak": fma_peak.get("ffma_rrr_tflops"), "unit": "TFLOP/s",
+                   "frac": (gb_tfs / fma_peak["ffma_rrr_tflops"]) if fma_peak.get("ffma_rrr_tflops") else None,
+                   "traffic": None, "peak_source": "measured in this run (benchmarks/fma_peak)",
+                   "hbm_gbs": gabor_bytes / (stage["gabor"] * 1e-3) / 1e9, "ms_per_step": stage["gabor"]}
+        line = {
+            "metric": METRIC, "value": total_imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: %d-image synthetic BSDS-shaped batch per GPU, 321x481 RGB, "
+                                   "bank 4 scales x 6 orientations, k-means k=8 T=20, BSD metrics vs 5 ground truths" % B,
+                       "images_per_step_per_gpu": B, "unique_images": unique, "group": args.group,
+                       "l2": "inputs + feature tensor (%.1f GB per step) far exceed the 126 MB L2" % (B * N * D * 4 / 1e9)},
+            "e2e": {"value": total_imgs / (e2e_ms * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": int(h_img.numel() + h_gt.numel() * 2 + h_idx.numel() * 4),
+                    "d2h_bytes_per_step": int(B * (8 + G * 8 * 8 + 2 * K_CLUSTERS * 4 + G * 4 + 4))},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof_km if dominant == "kmeans" else roof_gb,
+            "roofline_other": roof_gb if dominant == "kmeans" else roof_km,
+            "stage_ms_per_step": stage,
+            "fma_peak": fma_peak,
+            "dataset_scores": {k: float(sums[i] / sums[-1]) for i, k in enumerate(SUM_KEYS)},
+        }
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            n = max(threads, 4)
+            rate, dt = cpu_pipeline_rate(n, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                                    "sample": "%d images, one per host thread, %.1f s: C oracle (fp64 separable Gabor + "
+                                              "fp32-exact k-means + BSD metrics)" % (n, dt)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def measure_fma_peak():
+    exe = os.path.join(ROOT, "benchmarks", "fma_peak")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout.strip().splitlines()[-1]
+        return json.loads(out)
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=200, help="images per step per GPU")
+    ap.add_argument("--unique", type=int, default=48, help="distinct synthetic images generated per rank (cycled)")
+    ap.add_argument("--group", type=int, default=0, help="images per L2-resident group (0 = library default)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

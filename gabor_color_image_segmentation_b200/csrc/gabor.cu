@@ -1,0 +1,522 @@
+// gabor.cu — colour planes + multi-scale, multi-orientation Gabor bank -> feature planes.
+//
+// Reference: none.  BSD_metrics/script.py:30 is the segmenter slot; the reference fills it
+// with third-party SLIC and contains no filter-bank code, so this stage follows the spec in
+// DESIGN.md §3 (scikit-image gabor_kernel definition, sigma_x = sigma_y, reflect borders).
+//
+// Design.  With sigma_x = sigma_y the complex Gabor kernel is exactly
+// rank one: g[y][x] = gy[y] * gx[x] with complex 1-D factors, so one CTA computes a
+// 32-column strip of one (image, channel, scale) as a row pass into shared memory followed
+// by a column pass out of it, and never writes the intermediate to HBM.  Orientations
+// theta and pi - theta share the row pass (conjugate) and the four real column sums.
+// Both passes are register-blocked sliding-window FMA loops on the FP32 pipe (the stage is
+// FP32-bound, not HBM-bound: 45 MB vs 3.7 GFLOP per 321x481 image).
+#include <math.h>
+
+#include <algorithm>
+
+#include "gabor.cuh"
+
+namespace gcis {
+
+// ------------------------------------------------------------------------------------
+// Host: bank description
+// ------------------------------------------------------------------------------------
+
+double gabor_sigma(double frequency, double bandwidth)
+{
+    const double b = bandwidth;
+    return std::sqrt(std::log(2.0) / 2.0) / M_PI * (std::pow(2.0, b) + 1) / (std::pow(2.0, b) - 1) / frequency;
+}
+
+int gabor_half_width(double frequency, double theta, double bandwidth, double n_stds)
+{
+    const double s = gabor_sigma(frequency, bandwidth);
+    const double a = std::fabs(n_stds * s * std::cos(theta)), b = std::fabs(n_stds * s * std::sin(theta));
+    return (int)std::ceil(std::max(std::max(a, b), 1.0));
+}
+
+int gabor_separable(double frequency, double theta, double bandwidth, double n_stds, std::vector<double> &gx_re,
+                    std::vector<double> &gx_im, std::vector<double> &gy_re, std::vector<double> &gy_im)
+{
+    const double s = gabor_sigma(frequency, bandwidth);
+    const int h = gabor_half_width(frequency, theta, bandwidth, n_stds);
+    const double ct = std::cos(theta), st = std::sin(theta);
+    const double norm = 1.0 / (2.0 * M_PI * s * s);
+    gx_re.resize(2 * h + 1); gx_im.resize(2 * h + 1); gy_re.resize(2 * h + 1); gy_im.resize(2 * h + 1);
+    for (int t = 0; t <= 2 * h; ++t) {
+        const double x = t - h;
+        const double env = std::exp(-0.5 * x * x / (s * s));
+        const double px = 2.0 * M_PI * frequency * ct * x, py = 2.0 * M_PI * frequency * st * x;
+        gx_re[t] = env * std::cos(px);
+        gx_im[t] = env * std::sin(px);
+        gy_re[t] = env * std::cos(py) * norm;
+        gy_im[t] = env * std::sin(py) * norm;
+    }
+    return h;
+}
+
+static int push_taps(std::vector<float> &table, const std::vector<double> &g, bool allow_drop, double ref_max)
+{
+    double m = 0;
+    for (double v : g) m = std::max(m, std::fabs(v));
+    if (allow_drop && m <= 1e-12 * ref_max) return -1;
+    while (table.size() % 4) table.push_back(0.f);
+    const int off = (int)table.size();
+    table.insert(table.end(), GB_TAP_PAD, 0.f);
+    for (double v : g) table.push_back((float)v);
+    table.insert(table.end(), GB_TAP_PAD, 0.f);
+    return off;
+}
+
+int build_bank(const double *freqs, int S, const double *thetas, int O, double bandwidth, double n_stds,
+               GaborBankHost &out)
+{
+    if (S < 1 || S > GB_MAX_SCALES || O < 1 || O > 2 * GB_MAX_JOBS)
+        return set_error(GCIS_E_INVALID, "bank: n_scales=%d n_orient=%d unsupported", S, O);
+    out = GaborBankHost();
+    out.S = S; out.O = O;
+    out.scales.resize(S);
+    for (int s = 0; s < S; ++s) {
+        if (!(freqs[s] > 0)) return set_error(GCIS_E_INVALID, "bank: frequency[%d] <= 0", s);
+        GaborScale &sc = out.scales[s];
+        sc.n_jobs = 0; sc.hmax = 0;
+        std::vector<int> used(O, 0);
+        for (int o = 0; o < O; ++o) {
+            if (used[o]) continue;
+            used[o] = 1;
+            const int h = gabor_half_width(freqs[s], thetas[o], bandwidth, n_stds);
+            int partner = -1;
+            for (int o2 = o + 1; o2 < O; ++o2)
+                if (!used[o2] && std::fabs(thetas[o] + thetas[o2] - M_PI) < 1e-9 &&
+                    gabor_half_width(freqs[s], thetas[o2], bandwidth, n_stds) == h) {
+                    partner = o2;
+                    break;
+                }
+            if (partner >= 0) used[partner] = 1;
+            if (sc.n_jobs >= GB_MAX_JOBS) return set_error(GCIS_E_INVALID, "bank: too many jobs per scale");
+            std::vector<double> xr, xi, yr, yi;
+            gabor_separable(freqs[s], thetas[o], bandwidth, n_stds, xr, xi, yr, yi);
+            double mx = 0, my = 0;
+            for (double v : xr) mx = std::max(mx, std::fabs(v));
+            for (double v : yr) my = std::max(my, std::fabs(v));
+            GaborJob &j = sc.jobs[sc.n_jobs++];
+            j.h = h;
+            j.row_re = push_taps(out.taps, xr, false, mx);
+            j.row_im = push_taps(out.taps, xi, true, mx);
+            j.col_re = push_taps(out.taps, yr, false, my);
+            j.col_im = push_taps(out.taps, yi, true, my);
+            j.out0 = o; j.out1 = partner;
+            sc.hmax = std::max(sc.hmax, h);
+            const double K = 2 * h + 1;
+            const double row = K * (1 + (j.row_im >= 0));
+            const double col = K * (1 + (j.row_im >= 0)) * (1 + (j.col_im >= 0));
+            out.flops_per_pixel_channel += 2.0 * (row + col);
+        }
+        out.hmax = std::max(out.hmax, sc.hmax);
+    }
+    return GCIS_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// Device: colour planes with horizontal reflect padding
+// ------------------------------------------------------------------------------------
+
+namespace {
+
+__device__ __forceinline__ float srgb_to_linear(float v)
+{
+    return v <= 0.04045f ? v / 12.92f : powf((v + 0.055f) / 1.055f, 2.4f);
+}
+__device__ __forceinline__ float lab_f(float t)
+{
+    const float d = 6.0f / 29.0f;
+    return t > d * d * d ? cbrtf(t) : t / (3.0f * d * d) + 4.0f / 29.0f;
+}
+
+// img [B][H][W][3] u8 -> planes [B][3][H][Wp] f32; plane column cp holds image column
+// reflect(cp - P): the Gabor row pass then reads its halo without any border logic.
+__global__ void colour_pad_kernel(const uint8_t *__restrict__ img, float *__restrict__ planes, int B, int H, int W,
+                                  int P, int Wp, int space)
+{
+    const long long total = (long long)B * H * Wp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int cp = (int)(i % Wp);
+        const long long br = i / Wp;
+        const int r = (int)(br % H);
+        const int b = (int)(br / H);
+        const int c = reflect_index(cp - P, W);
+        const uint8_t *px = img + (((size_t)b * H + r) * W + c) * 3;
+        float R = px[0] * (1.0f / 255.0f), G = px[1] * (1.0f / 255.0f), Bl = px[2] * (1.0f / 255.0f);
+        float o0, o1, o2;
+        if (space == GCIS_COLOUR_RGB) {
+            o0 = R; o1 = G; o2 = Bl;
+        } else if (space == GCIS_COLOUR_OPPONENT) {
+            o0 = (R - G) * 0.70710678118654752f;
+            o1 = (R + G - 2.0f * Bl) * 0.40824829046386302f;
+            o2 = (R + G + Bl) * 0.57735026918962576f;
+        } else {
+            const float lr = srgb_to_linear(R), lg = srgb_to_linear(G), lb = srgb_to_linear(Bl);
+            const float X = (0.4124564f * lr + 0.3575761f * lg + 0.1804375f * lb) / 0.95047f;
+            const float Y = (0.2126729f * lr + 0.7151522f * lg + 0.0721750f * lb);
+            const float Z = (0.0193339f * lr + 0.1191920f * lg + 0.9503041f * lb) / 1.08883f;
+            const float fx = lab_f(X), fy = lab_f(Y), fz = lab_f(Z);
+            o0 = (116.0f * fy - 16.0f) / 100.0f;
+            o1 = 500.0f * (fx - fy) / 100.0f;
+            o2 = 200.0f * (fy - fz) / 100.0f;
+        }
+        const size_t plane = (size_t)H * Wp;
+        float *dst = planes + (size_t)b * 3 * plane + (size_t)r * Wp + cp;
+        dst[0] = o0; dst[plane] = o1; dst[2 * plane] = o2;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Device: the bank
+// ------------------------------------------------------------------------------------
+
+constexpr int GB_TW = 32;        // strip width = one warp of columns
+constexpr int GB_TWP = 33;       // odd stride: row-pass writes (lane = row) and column-pass reads conflict-free
+constexpr int GB_THREADS = 256;
+constexpr int GB_WARPS = GB_THREADS / 32;
+constexpr int GB_RC = 8;         // column pass: output rows per thread
+constexpr int GB_RR = 4;         // row pass: output columns per thread (32 / 4 = 8 column blocks = 8 warps)
+constexpr int GB_CHUNK = 32;     // input rows staged per row-pass step (lane = row)
+
+struct GaborParams {
+    const float *planes;   // [B][C][H][Wp]
+    float *feat;           // [B][C*S*O][H][W]
+    const float *taps;
+    const GaborScale *scales;
+    int B, C, H, W, Wp, P, S, O, feature;
+    int n_strips;
+    int TH[GB_MAX_SCALES];       // output rows per CTA at scale s
+    int n_vt[GB_MAX_SCALES];     // vertical tiles at scale s
+    int first_block[GB_MAX_SCALES + 1];  // block ranges ordered from the widest scale to the narrowest
+    int order[GB_MAX_SCALES];    // scale handled by range i
+    int nsrc_cap;                // rows of T the shared buffer holds
+    int istr;                    // chunk row stride (odd)
+    int tap_slot;                // floats reserved per tap array in shared memory
+    int rowtab_cap;
+};
+
+// out[i] += sum_u g[i + 2h - u] * x[u],  i < R, u < nsteps: the register-blocked sliding window
+// both passes share.  g is stored zero-padded (GB_TAP_PAD each side); every R steps the window
+// of 2R-1 taps slides by R with aligned 128-bit shared loads.
+template <int R, bool XI, bool GI, class XLoad>
+__device__ __forceinline__ void sweep(XLoad xload, const float *gr, const float *gi, int h, float (&A)[R],
+                                      float (&Bv)[R], float (&Cv)[R], float (&Dv)[R])
+{
+    float wr[2 * R - 1], wi[2 * R - 1];
+    int idx = GB_TAP_PAD + 2 * h - R + 1;
+#pragma unroll
+    for (int t = 0; t < 2 * R - 1; ++t) {
+        wr[t] = gr[idx + t];
+        wi[t] = GI ? gi[idx + t] : 0.f;
+    }
+    const int nsteps = (2 * h + R + R - 1) / R * R;
+#pragma unroll 1
+    for (int ub = 0; ub < nsteps; ub += R) {
+        if (ub) {
+#pragma unroll
+            for (int t = 2 * R - 2; t >= R; --t) {
+                wr[t] = wr[t - R];
+                if (GI) wi[t] = wi[t - R];
+            }
+            idx -= R;
+#pragma unroll
+            for (int t = 0; t < R; t += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(gr + idx + t);
+                wr[t] = v.x; wr[t + 1] = v.y; wr[t + 2] = v.z; wr[t + 3] = v.w;
+                if (GI) {
+                    const float4 q = *reinterpret_cast<const float4 *>(gi + idx + t);
+                    wi[t] = q.x; wi[t + 1] = q.y; wi[t + 2] = q.z; wi[t + 3] = q.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int uu = 0; uu < R; ++uu) {
+            float xr, xi;
+            xload(ub + uu, xr, xi);
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int t = i - uu + R - 1;
+                A[i] = fmaf(wr[t], xr, A[i]);
+                if (XI) Cv[i] = fmaf(wr[t], xi, Cv[i]);
+                if (GI) Dv[i] = fmaf(wi[t], xr, Dv[i]);
+                if (XI && GI) Bv[i] = fmaf(wi[t], xi, Bv[i]);
+            }
+        }
+    }
+}
+
+template <bool GI>
+__device__ __forceinline__ void row_pass_chunk(const float *chunk, int istr, const float *gr, const float *gi, int h,
+                                               float *Tre, float *Tim, int trow, bool active)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xb = warp * GB_RR;
+    float A[GB_RR], Bv[GB_RR], Cv[GB_RR], Dv[GB_RR];
+#pragma unroll
+    for (int i = 0; i < GB_RR; ++i) { A[i] = 0.f; Bv[i] = 0.f; Cv[i] = 0.f; Dv[i] = 0.f; }
+    const float *src = chunk + lane * istr + xb;
+    sweep<GB_RR, false, GI>([&](int u, float &xr, float &xi) { xr = src[u]; xi = 0.f; }, gr, gi, h, A, Bv, Cv, Dv);
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < GB_RR; ++i) {
+            Tre[trow * GB_TWP + xb + i] = A[i];
+            if (GI) Tim[trow * GB_TWP + xb + i] = Dv[i];
+        }
+    }
+}
+
+template <bool XI, bool GI>
+__device__ __forceinline__ void col_pass(const GaborParams &P, const float *Tre, const float *Tim, const int *rowtab,
+                                         const float *gr, const float *gi, int h, int y0, int th, int x0,
+                                         float *feat0, float *feat1)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nrb = (th + GB_RC - 1) / GB_RC;
+    const bool col_ok = x0 + lane < P.W;
+    for (int rb = warp; rb < nrb; rb += GB_WARPS) {
+        float A[GB_RC], Bv[GB_RC], Cv[GB_RC], Dv[GB_RC];
+#pragma unroll
+        for (int i = 0; i < GB_RC; ++i) { A[i] = 0.f; Bv[i] = 0.f; Cv[i] = 0.f; Dv[i] = 0.f; }
+        const int *rt = rowtab + rb * GB_RC;
+        sweep<GB_RC, XI, GI>(
+            [&](int u, float &xr, float &xi) {
+                const int o = rt[u] + lane;
+                xr = Tre[o];
+                xi = XI ? Tim[o] : 0.f;
+            },
+            gr, gi, h, A, Bv, Cv, Dv);
+#pragma unroll
+        for (int i = 0; i < GB_RC; ++i) {
+            const int r = rb * GB_RC + i;
+            if (r < th && col_ok) {
+                // theta: (A - B) + i(C + D);  pi - theta: (A + B) + i(D - C)
+                const float re0 = A[i] - Bv[i], im0 = Cv[i] + Dv[i];
+                float e0 = fmaf(re0, re0, im0 * im0);
+                const size_t o = (size_t)(y0 + r) * P.W + x0 + lane;
+                feat0[o] = P.feature == GCIS_FEATURE_MAGNITUDE ? sqrtf(e0) : e0;
+                if (feat1) {
+                    const float re1 = A[i] + Bv[i], im1 = Dv[i] - Cv[i];
+                    float e1 = fmaf(re1, re1, im1 * im1);
+                    feat1[o] = P.feature == GCIS_FEATURE_MAGNITUDE ? sqrtf(e1) : e1;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_constant__ GaborParams P)
+{
+    extern __shared__ __align__(16) float smem[];
+    __shared__ int s_lo, s_hi;
+
+    // ---- decode the work item: ranges are ordered widest scale first ----
+    int range = 0;
+    while (range + 1 < P.S && (int)blockIdx.x >= P.first_block[range + 1]) ++range;
+    const int s = P.order[range];
+    int rem = blockIdx.x - P.first_block[range];
+    const int nvt = P.n_vt[s];
+    const int vt = rem % nvt; rem /= nvt;
+    const int strip = rem % P.n_strips; rem /= P.n_strips;
+    const int c = rem % P.C;
+    const int b = rem / P.C;
+    const int x0 = strip * GB_TW;
+    const int y0 = vt * P.TH[s];
+    const int th = min(P.TH[s], P.H - y0);
+
+    float *tapbuf = smem;  // first, so the 128-bit tap loads stay 16-byte aligned
+    int *rowtab = reinterpret_cast<int *>(tapbuf + 4 * P.tap_slot);
+    float *Tre = reinterpret_cast<float *>(rowtab + P.rowtab_cap);
+    float *Tim = Tre + (size_t)P.nsrc_cap * GB_TWP;
+    float *chunk = Tim + (size_t)P.nsrc_cap * GB_TWP;
+
+    const GaborScale &sc = P.scales[s];
+    const float *plane = P.planes + ((size_t)b * P.C + c) * P.H * P.Wp;
+    const int D = P.C * P.S * P.O;
+    float *featb = P.feat + (size_t)b * D * P.H * P.W;
+    const int lane = threadIdx.x & 31;
+
+    for (int ji = 0; ji < sc.n_jobs; ++ji) {
+        const GaborJob job = sc.jobs[ji];
+        const int h = job.h;
+        const int ntap = 2 * h + 1 + 2 * GB_TAP_PAD;
+        // tap arrays are placed so that the sweep's 128-bit window loads are aligned
+        const int shift = (4 - ((2 * h + 1) & 3)) & 3;
+        float *t_rr = tapbuf + shift, *t_ri = t_rr + P.tap_slot, *t_cr = t_ri + P.tap_slot, *t_ci = t_cr + P.tap_slot;
+        __syncthreads();  // previous job's column pass is done with T, taps and rowtab
+        if (threadIdx.x == 0) { s_lo = P.H; s_hi = 0; }
+        for (int i = threadIdx.x; i < ntap; i += GB_THREADS) {
+            t_rr[i] = P.taps[job.row_re + i];
+            t_ri[i] = job.row_im >= 0 ? P.taps[job.row_im + i] : 0.f;
+            t_cr[i] = P.taps[job.col_re + i];
+            t_ci[i] = job.col_im >= 0 ? P.taps[job.col_im + i] : 0.f;
+        }
+        __syncthreads();
+        // rows of the image the column pass will touch (reflect-folded), and their span
+        const int ne = (th + GB_RC - 1) / GB_RC * GB_RC + 2 * h + 2 * GB_RC;
+        {
+            int lo = P.H, hi = 0;
+            for (int e = threadIdx.x; e < ne; e += GB_THREADS) {
+                const int r = reflect_index(y0 - h + min(e, th + 2 * h - 1), P.H);
+                rowtab[e] = r;
+                lo = min(lo, r); hi = max(hi, r + 1);
+            }
+            lo = __reduce_min_sync(0xffffffffu, lo);
+            hi = __reduce_max_sync(0xffffffffu, hi);
+            if (lane == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+        }
+        __syncthreads();
+        const int lo = s_lo, hi = s_hi;
+        for (int e = threadIdx.x; e < ne; e += GB_THREADS) rowtab[e] = (rowtab[e] - lo) * GB_TWP;
+
+        // ---- row pass: image rows [lo, hi) -> T (complex) in shared memory ----
+        const int cw = GB_TW + 2 * h + GB_RR;            // staged columns per row
+        const int gcol0 = x0 - h + P.P;                  // first staged column in the padded plane
+        for (int ch0 = lo; ch0 < hi; ch0 += GB_CHUNK) {
+            __syncthreads();                             // chunk buffer free (and rowtab complete on 1st pass)
+            for (int i = threadIdx.x; i < GB_CHUNK * cw; i += GB_THREADS) {
+                const int rr = i / cw, cc = i - rr * cw;
+                const int r = ch0 + rr, gc = gcol0 + cc;
+                chunk[rr * P.istr + cc] = (r < hi && gc < P.Wp) ? plane[(size_t)r * P.Wp + gc] : 0.f;
+            }
+            __syncthreads();
+            const int trow = ch0 - lo + lane;
+            const bool active = ch0 + lane < hi;
+            if (job.row_im >= 0) row_pass_chunk<true>(chunk, P.istr, t_rr, t_ri, h, Tre, Tim, trow, active);
+            else row_pass_chunk<false>(chunk, P.istr, t_rr, t_ri, h, Tre, Tim, trow, active);
+        }
+        __syncthreads();
+
+        // ---- column pass: T -> |response| for theta (and pi - theta) ----
+        const int d0 = (c * P.S + s) * P.O;
+        float *f0 = featb + (size_t)(d0 + job.out0) * P.H * P.W;
+        float *f1 = job.out1 >= 0 ? featb + (size_t)(d0 + job.out1) * P.H * P.W : nullptr;
+        const bool xi = job.row_im >= 0, gi = job.col_im >= 0;
+        if (xi && gi) col_pass<true, true>(P, Tre, Tim, rowtab, t_cr, t_ci, h, y0, th, x0, f0, f1);
+        else if (xi) col_pass<true, false>(P, Tre, Tim, rowtab, t_cr, t_ci, h, y0, th, x0, f0, f1);
+        else if (gi) col_pass<false, true>(P, Tre, Tim, rowtab, t_cr, t_ci, h, y0, th, x0, f0, f1);
+        else col_pass<false, false>(P, Tre, Tim, rowtab, t_cr, t_ci, h, y0, th, x0, f0, f1);
+    }
+}
+
+}  // namespace
+
+int colour_planes_launch(const uint8_t *d_img, float *d_planes, int B, int H, int W, int P, int Wp, int space,
+                         cudaStream_t st)
+{
+    const long long total = (long long)B * H * Wp;
+    const int threads = 256;
+    const int blocks = (int)std::min<long long>((total + threads - 1) / threads, 148 * 16);
+    colour_pad_kernel<<<blocks, threads, 0, st>>>(d_img, d_planes, B, H, W, P, Wp, space);
+    GCIS_LAUNCH_CHECK();
+    return GCIS_OK;
+}
+
+// Shared-memory plan for the bank kernel on an H x W image.
+struct GaborLaunchPlan {
+    GaborParams p;
+    size_t smem = 0;
+    int blocks = 0;
+};
+
+static size_t gabor_smem_bytes(int nsrc, int hmax, int th_max)
+{
+    const int istr = (GB_TW + 2 * hmax + GB_RR) | 1;
+    const int tap_slot = ((2 * hmax + 1 + 2 * GB_TAP_PAD + 3 + 3) / 4) * 4;
+    const int rowtab = round_up((th_max + GB_RC - 1) / GB_RC * GB_RC + 2 * hmax + 2 * GB_RC, 4);
+    return sizeof(float) * ((size_t)2 * nsrc * GB_TWP + (size_t)GB_CHUNK * istr + 4 * (size_t)tap_slot) +
+           sizeof(int) * (size_t)rowtab;
+}
+
+int gabor_plan(const GaborBankHost &bank, int H, int W, int C, int P, int Wp, int feature, GaborLaunchPlan &lp)
+{
+    GaborParams &p = lp.p;
+    memset(&p, 0, sizeof(p));
+    p.C = C; p.H = H; p.W = W; p.Wp = Wp; p.P = P; p.S = bank.S; p.O = bank.O; p.feature = feature;
+    p.n_strips = ceil_div(W, GB_TW);
+    const int hmax = bank.hmax;
+    const size_t two_per_sm = 113 * 1024, one_per_sm = 227 * 1024;
+    size_t budget;
+    int nsrc_cap;
+    if (gabor_smem_bytes(H, hmax, H) <= one_per_sm) {
+        // whole image height per CTA: the row pass is never recomputed for a vertical halo
+        nsrc_cap = H;
+        for (int s = 0; s < bank.S; ++s) { p.TH[s] = H; p.n_vt[s] = 1; }
+        budget = gabor_smem_bytes(H, hmax, H);
+    } else {
+        budget = two_per_sm;
+        nsrc_cap = 0;
+        for (int rows = 2 * hmax + GB_RC; gabor_smem_bytes(rows, hmax, rows) <= budget; rows += GB_RC) nsrc_cap = rows;
+        if (nsrc_cap == 0) {
+            budget = one_per_sm;
+            for (int rows = 2 * hmax + GB_RC; gabor_smem_bytes(rows, hmax, rows) <= budget; rows += GB_RC) nsrc_cap = rows;
+        }
+        if (nsrc_cap == 0) return set_error(GCIS_E_INVALID, "gabor: kernel half-width %d too large for shared memory", hmax);
+        for (int s = 0; s < bank.S; ++s) {
+            const int hs = bank.scales[s].hmax;
+            int th = (nsrc_cap - 2 * hs) / GB_RC * GB_RC;
+            if (th < GB_RC) th = GB_RC;
+            if (th > H) th = H;
+            p.n_vt[s] = ceil_div(H, th);
+            p.TH[s] = round_up(ceil_div(H, p.n_vt[s]), GB_RC);  // balance the tiles
+            if (p.TH[s] > th) p.TH[s] = th;
+            p.n_vt[s] = ceil_div(H, p.TH[s]);
+        }
+    }
+    int th_max = 0;
+    for (int s = 0; s < bank.S; ++s) th_max = std::max(th_max, p.TH[s]);
+    p.nsrc_cap = nsrc_cap;
+    p.istr = (GB_TW + 2 * hmax + GB_RR) | 1;
+    p.tap_slot = ((2 * hmax + 1 + 2 * GB_TAP_PAD + 3 + 3) / 4) * 4;
+    p.rowtab_cap = round_up((th_max + GB_RC - 1) / GB_RC * GB_RC + 2 * hmax + 2 * GB_RC, 4);
+    lp.smem = gabor_smem_bytes(nsrc_cap, hmax, th_max);
+    // widest scale first so the long CTAs are not left for the tail
+    std::vector<int> order(bank.S);
+    for (int s = 0; s < bank.S; ++s) order[s] = s;
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int a, int b) { return bank.scales[a].hmax > bank.scales[b].hmax; });
+    for (int i = 0; i < bank.S; ++i) p.order[i] = order[i];
+    return GCIS_OK;
+}
+
+GaborLaunchPlan *gabor_plan_new(const GaborBankHost &bank, int H, int W, int C, int P, int Wp, int feature, size_t *smem)
+{
+    GaborLaunchPlan *lp = new GaborLaunchPlan();
+    if (gabor_plan(bank, H, W, C, P, Wp, feature, *lp)) {
+        delete lp;
+        return nullptr;
+    }
+    if (smem) *smem = lp->smem;
+    return lp;
+}
+
+void gabor_plan_delete(GaborLaunchPlan *lp) { delete lp; }
+
+int gabor_launch(GaborLaunchPlan &lp, const float *d_planes, float *d_feat, const float *d_taps,
+                 const GaborScale *d_scales, int B, cudaStream_t st)
+{
+    GaborParams &p = lp.p;
+    p.planes = d_planes; p.feat = d_feat; p.taps = d_taps; p.scales = d_scales; p.B = B;
+    int acc = 0;
+    for (int i = 0; i < p.S; ++i) {
+        p.first_block[i] = acc;
+        acc += B * p.C * p.n_strips * p.n_vt[p.order[i]];
+    }
+    p.first_block[p.S] = acc;
+    lp.blocks = acc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GCIS_CUDA_TRY(cudaFuncSetAttribute(gabor_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    gabor_bank_kernel<<<acc, GB_THREADS, lp.smem, st>>>(p);
+    GCIS_LAUNCH_CHECK();
+    return GCIS_OK;
+}
+
+}  // namespace gcis

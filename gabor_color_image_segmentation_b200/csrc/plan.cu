@@ -1,0 +1,489 @@
+// plan.cu — the C ABI (include/gcis.h): plan object, stage entry points and the batch driver.
+//
+// The batch driver stands behind the reference's driver loop (BSD_metrics/script.py:22-38):
+// segment every image, then score it against its ground truths.  Images are processed in
+// small groups so that one group's feature tensor (44.5 MB per 321x481 image) stays in the
+// 126 MB L2 across the k-means iterations instead of being re-streamed from HBM.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "gabor.cuh"
+
+namespace gcis {
+
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+
+int set_error(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+// implemented in the stage files
+struct GaborLaunchPlan;
+int colour_planes_launch(const uint8_t *, float *, int, int, int, int, int, int, cudaStream_t);
+int label_metrics_launch(const int32_t *, const uint16_t *, const int32_t *, int, int, int, int, int, int, int,
+                         int64_t *, int64_t *, int32_t *, int32_t *, int32_t *, int32_t *, int32_t *, int32_t *,
+                         cudaStream_t);
+int find_boundaries_launch(const int32_t *, uint8_t *, int, int, int, cudaStream_t);
+size_t kmeans_workspace_bytes(int B, int D, int k);
+int kmeans_launch(const float *, int, int, int, int, int, int, const int32_t *, int32_t *, float *, void *,
+                  cudaStream_t);
+GaborLaunchPlan *gabor_plan_new(const GaborBankHost &, int H, int W, int C, int P, int Wp, int feature, size_t *smem);
+void gabor_plan_delete(GaborLaunchPlan *);
+int gabor_launch(GaborLaunchPlan &, const float *, float *, const float *, const GaborScale *, int, cudaStream_t);
+
+}  // namespace gcis
+
+using namespace gcis;
+
+struct gcis_plan {
+    gcis_config cfg;
+    std::vector<double> freqs, thetas;
+    GaborBankHost bank;
+    GaborLaunchPlan *glp = nullptr;
+    int D = 0, N = 0, P = 0, Wp = 0, group = 1;
+    size_t bytes = 0;
+    // device workspaces
+    float *d_taps = nullptr;
+    GaborScale *d_scales = nullptr;
+    float *d_planes = nullptr;   // [group][3][H][Wp]
+    float *d_feat = nullptr;     // [group][D][N]
+    void *d_km_ws = nullptr;
+    int32_t *d_labels = nullptr; // [max_batch][N]
+    int64_t *d_bd_count = nullptr, *d_gt_counts = nullptr;
+    int32_t *d_area = nullptr, *d_perim = nullptr, *d_hist = nullptr, *d_n_seg = nullptr, *d_n_lab = nullptr,
+            *d_status = nullptr;
+    // device input staging for the host entry point
+    uint8_t *d_img = nullptr;
+    uint16_t *d_gt = nullptr;
+    int32_t *d_n_gt = nullptr, *d_init = nullptr;
+    cudaStream_t stream = nullptr;
+    // profiling
+    bool profiling = false;
+    std::vector<cudaEvent_t> events;  // 5 per group: colour | gabor | kmeans | (metrics: 2 at the end)
+    float stage_ms[4] = {0, 0, 0, 0};
+    int n_groups_last = 0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(T **p, size_t n, size_t *total)
+{
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), bytes);
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        return set_error(e == cudaErrorMemoryAllocation ? GCIS_E_NOMEM : GCIS_E_CUDA, "cudaMalloc(%zu) -> %s", bytes,
+                         cudaGetErrorString(e));
+    }
+    *total += bytes;
+    return GCIS_OK;
+}
+
+#define TRY(x)                 \
+    do {                       \
+        int _rc = (x);         \
+        if (_rc) return _rc;   \
+    } while (0)
+
+int plan_check_batch(const gcis_plan *p, int B)
+{
+    if (!p) return set_error(GCIS_E_INVALID, "null plan");
+    if (B < 1 || B > p->cfg.max_batch) return set_error(GCIS_E_INVALID, "B=%d outside 1..max_batch=%d", B, p->cfg.max_batch);
+    return GCIS_OK;
+}
+
+cudaEvent_t plan_event(gcis_plan *p, size_t i)
+{
+    while (p->events.size() <= i) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        p->events.push_back(e);
+    }
+    return p->events[i];
+}
+
+// colour -> Gabor -> k-means for one group of images whose features live in plan->d_feat.
+int segment_group(gcis_plan *p, const uint8_t *d_img, int nb, const int32_t *d_init, int32_t *d_labels,
+                  float *d_feat_out, cudaStream_t st, int group_index)
+{
+    const gcis_config &c = p->cfg;
+    float *feat = d_feat_out ? d_feat_out : p->d_feat;
+    const bool prof = p->profiling && group_index >= 0;
+    if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 0), st);
+    TRY(colour_planes_launch(d_img, p->d_planes, nb, c.height, c.width, p->P, p->Wp, c.colour_space, st));
+    if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 1), st);
+    TRY(gabor_launch(*p->glp, p->d_planes, feat, p->d_taps, p->d_scales, nb, st));
+    if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 2), st);
+    if (d_labels) {
+        TRY(kmeans_launch(feat, nb, p->D, p->N, c.k, c.iters, c.fix_shift, d_init, d_labels, nullptr, p->d_km_ws, st));
+        if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 3), st);
+    }
+    return GCIS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t gcis_version(void) { return GCIS_VERSION; }
+const char *gcis_last_error(void) { return g_last_error.c_str(); }
+int64_t gcis_launch_count(void) { return g_launches.load(); }
+
+int32_t gcis_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return set_error(GCIS_E_CUDA, "cudaGetDeviceCount -> %s", cudaGetErrorString(e));
+    return n;
+}
+
+int32_t gcis_gabor_half_width(double frequency, double theta, double bandwidth, double n_stds)
+{
+    if (!(frequency > 0) || !(bandwidth > 0) || !(n_stds > 0)) return set_error(GCIS_E_INVALID, "gabor: bad parameters");
+    return gabor_half_width(frequency, theta, bandwidth, n_stds);
+}
+
+int32_t gcis_gabor_separable(double frequency, double theta, double bandwidth, double n_stds, double *gx_re,
+                             double *gx_im, double *gy_re, double *gy_im, int32_t cap_taps)
+{
+    if (!(frequency > 0) || !(bandwidth > 0) || !(n_stds > 0)) return set_error(GCIS_E_INVALID, "gabor: bad parameters");
+    std::vector<double> a, b, c, d;
+    const int h = gabor_separable(frequency, theta, bandwidth, n_stds, a, b, c, d);
+    if (2 * h + 1 > cap_taps) return set_error(GCIS_E_INVALID, "gabor: %d taps needed, capacity %d", 2 * h + 1, cap_taps);
+    memcpy(gx_re, a.data(), sizeof(double) * a.size());
+    memcpy(gx_im, b.data(), sizeof(double) * b.size());
+    memcpy(gy_re, c.data(), sizeof(double) * c.size());
+    memcpy(gy_im, d.data(), sizeof(double) * d.size());
+    return h;
+}
+
+int32_t gcis_plan_create(const gcis_config *cfg, gcis_plan **out)
+{
+    if (!cfg || !out) return set_error(GCIS_E_INVALID, "plan: null argument");
+    *out = nullptr;
+    if (cfg->height < 1 || cfg->width < 1 || cfg->max_batch < 1)
+        return set_error(GCIS_E_INVALID, "plan: bad shape H=%d W=%d max_batch=%d", cfg->height, cfg->width, cfg->max_batch);
+    if ((int64_t)cfg->height * cfg->width > (1 << 30)) return set_error(GCIS_E_INVALID, "plan: image too large");
+    if (!cfg->frequencies || !cfg->thetas) return set_error(GCIS_E_INVALID, "plan: null bank");
+    if (cfg->colour_space < 0 || cfg->colour_space > 2) return set_error(GCIS_E_INVALID, "plan: colour_space=%d", cfg->colour_space);
+    if (cfg->feature < 0 || cfg->feature > 1) return set_error(GCIS_E_INVALID, "plan: feature=%d", cfg->feature);
+    if (cfg->k < 1 || cfg->k > 32) return set_error(GCIS_E_INVALID, "plan: k=%d outside 1..32", cfg->k);
+    if (cfg->iters < 1) return set_error(GCIS_E_INVALID, "plan: iters=%d", cfg->iters);
+    if (cfg->max_gt < 0 || cfg->n_lab_cap < 1) return set_error(GCIS_E_INVALID, "plan: max_gt=%d n_lab_cap=%d", cfg->max_gt, cfg->n_lab_cap);
+    if (!(cfg->bandwidth > 0) || !(cfg->n_stds > 0)) return set_error(GCIS_E_INVALID, "plan: bandwidth/n_stds");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return set_error(GCIS_E_CUDA, "plan: no CUDA device (this library has no CPU path)");
+
+    gcis_plan *p = new gcis_plan();
+    p->cfg = *cfg;
+    p->freqs.assign(cfg->frequencies, cfg->frequencies + cfg->n_scales);
+    p->thetas.assign(cfg->thetas, cfg->thetas + cfg->n_orient);
+    p->cfg.frequencies = p->freqs.data();
+    p->cfg.thetas = p->thetas.data();
+    if (p->cfg.fix_shift <= 0) p->cfg.fix_shift = 24;
+    if (p->cfg.dil_recall <= 0) p->cfg.dil_recall = 5;
+    int rc = build_bank(p->freqs.data(), cfg->n_scales, p->thetas.data(), cfg->n_orient, cfg->bandwidth, cfg->n_stds, p->bank);
+    if (rc) { delete p; return rc; }
+    const int H = cfg->height, W = cfg->width;
+    p->N = H * W;
+    p->D = 3 * cfg->n_scales * cfg->n_orient;
+    p->P = p->bank.hmax;
+    p->Wp = round_up(W + 2 * p->P + 8, 4);
+    int group = cfg->group;
+    if (const char *e = getenv("GCIS_GROUP")) group = atoi(e);
+    if (group <= 0) group = 2;
+    p->group = std::min(group, cfg->max_batch);
+    size_t smem = 0;
+    p->glp = gabor_plan_new(p->bank, H, W, 3, p->P, p->Wp, cfg->feature, &smem);
+    if (!p->glp) { delete p; return GCIS_E_INVALID; }
+
+    const size_t MB = cfg->max_batch, G = std::max(cfg->max_gt, 1), k = cfg->k;
+    auto fail = [&](int code) { gcis_plan_destroy(p); return code; };
+#define PA(ptr, n)                                        \
+    do {                                                  \
+        int _rc = dev_alloc(&(ptr), (n), &p->bytes);      \
+        if (_rc) return fail(_rc);                        \
+    } while (0)
+    PA(p->d_taps, p->bank.taps.size());
+    PA(p->d_scales, p->bank.scales.size());
+    PA(p->d_planes, (size_t)p->group * 3 * H * p->Wp);
+    PA(p->d_feat, (size_t)p->group * p->D * p->N);
+    {
+        char *ws = nullptr;
+        int rc2 = dev_alloc(&ws, kmeans_workspace_bytes(p->group, p->D, cfg->k), &p->bytes);
+        if (rc2) return fail(rc2);
+        p->d_km_ws = ws;
+    }
+    PA(p->d_labels, MB * p->N);
+    PA(p->d_bd_count, MB);
+    PA(p->d_gt_counts, MB * G * GCIS_GT_SLOTS);
+    PA(p->d_area, MB * k);
+    PA(p->d_perim, MB * k);
+    PA(p->d_hist, MB * G * k * cfg->n_lab_cap);
+    PA(p->d_n_seg, MB);
+    PA(p->d_n_lab, MB * G);
+    PA(p->d_status, MB);
+#undef PA
+    if (cudaMemcpy(p->d_taps, p->bank.taps.data(), sizeof(float) * p->bank.taps.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p->d_scales, p->bank.scales.data(), sizeof(GaborScale) * p->bank.scales.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error(GCIS_E_CUDA, "plan: uploading the bank failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(GCIS_E_CUDA);
+    }
+    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error(GCIS_E_CUDA, "plan: cudaStreamCreate failed");
+        return fail(GCIS_E_CUDA);
+    }
+    *out = p;
+    return GCIS_OK;
+}
+
+void gcis_plan_destroy(gcis_plan *p)
+{
+    if (!p) return;
+    cudaFree(p->d_taps); cudaFree(p->d_scales); cudaFree(p->d_planes); cudaFree(p->d_feat); cudaFree(p->d_km_ws);
+    cudaFree(p->d_labels); cudaFree(p->d_bd_count); cudaFree(p->d_gt_counts); cudaFree(p->d_area); cudaFree(p->d_perim);
+    cudaFree(p->d_hist); cudaFree(p->d_n_seg); cudaFree(p->d_n_lab); cudaFree(p->d_status);
+    cudaFree(p->d_img); cudaFree(p->d_gt); cudaFree(p->d_n_gt); cudaFree(p->d_init);
+    for (cudaEvent_t e : p->events) cudaEventDestroy(e);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    gabor_plan_delete(p->glp);
+    delete p;
+}
+
+int32_t gcis_plan_feature_dim(const gcis_plan *p) { return p ? p->D : set_error(GCIS_E_INVALID, "null plan"); }
+int64_t gcis_plan_workspace_bytes(const gcis_plan *p) { return p ? (int64_t)p->bytes : 0; }
+
+int32_t gcis_plan_set_profiling(gcis_plan *p, int32_t on)
+{
+    if (!p) return set_error(GCIS_E_INVALID, "null plan");
+    p->profiling = on != 0;
+    return GCIS_OK;
+}
+
+int32_t gcis_plan_last_stage_ms(gcis_plan *p, float *ms4)
+{
+    if (!p || !ms4) return set_error(GCIS_E_INVALID, "null argument");
+    memcpy(ms4, p->stage_ms, sizeof(p->stage_ms));
+    return GCIS_OK;
+}
+
+int32_t gcis_gabor_features(gcis_plan *p, const uint8_t *d_img, int32_t B, float *d_feat, void *stream)
+{
+    TRY(plan_check_batch(p, B));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t img_stride = (size_t)p->N * 3, feat_stride = (size_t)p->D * p->N;
+    for (int b0 = 0; b0 < B; b0 += p->group) {
+        const int nb = std::min(p->group, B - b0);
+        TRY(segment_group(p, d_img + b0 * img_stride, nb, nullptr, nullptr, d_feat + b0 * feat_stride, st, -1));
+    }
+    return GCIS_OK;
+}
+
+int32_t gcis_kmeans(gcis_plan *p, const float *d_feat, int32_t B, const int32_t *d_init_idx, int32_t *d_labels,
+                    float *d_centroids, void *stream)
+{
+    TRY(plan_check_batch(p, B));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const gcis_config &c = p->cfg;
+    const size_t feat_stride = (size_t)p->D * p->N;
+    for (int b0 = 0; b0 < B; b0 += p->group) {
+        const int nb = std::min(p->group, B - b0);
+        TRY(kmeans_launch(d_feat + b0 * feat_stride, nb, p->D, p->N, c.k, c.iters, c.fix_shift, d_init_idx + (size_t)b0 * c.k,
+                          d_labels + (size_t)b0 * p->N, d_centroids ? d_centroids + (size_t)b0 * c.k * p->D : nullptr,
+                          p->d_km_ws, st));
+    }
+    return GCIS_OK;
+}
+
+int32_t gcis_segment_device(gcis_plan *p, const uint8_t *d_img, int32_t B, const int32_t *d_init_idx,
+                            int32_t *d_labels, void *stream)
+{
+    TRY(plan_check_batch(p, B));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t img_stride = (size_t)p->N * 3;
+    int gi = 0;
+    for (int b0 = 0; b0 < B; b0 += p->group, ++gi) {
+        const int nb = std::min(p->group, B - b0);
+        TRY(segment_group(p, d_img + b0 * img_stride, nb, d_init_idx + (size_t)b0 * p->cfg.k, d_labels + (size_t)b0 * p->N,
+                          nullptr, st, gi));
+    }
+    p->n_groups_last = gi;
+    return GCIS_OK;
+}
+
+int32_t gcis_label_metrics_device(const int32_t *d_lb, const uint16_t *d_gt, const int32_t *d_n_gt, int32_t B,
+                                  int32_t H, int32_t W, int32_t G, int32_t n_seg_cap, int32_t n_lab_cap,
+                                  int32_t dil_recall, int64_t *d_bd_count, int64_t *d_gt_counts, int32_t *d_area,
+                                  int32_t *d_perim, int32_t *d_hist, int32_t *d_n_seg, int32_t *d_n_lab,
+                                  int32_t *d_status, void *stream)
+{
+    return label_metrics_launch(d_lb, d_gt, d_n_gt, B, H, W, G, n_seg_cap, n_lab_cap, dil_recall, d_bd_count,
+                                d_gt_counts, d_area, d_perim, d_hist, d_n_seg, d_n_lab, d_status,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int32_t gcis_label_metrics_host(const int32_t *h_lb, const uint16_t *h_gt, const int32_t *h_n_gt, int32_t B, int32_t H,
+                                int32_t W, int32_t G, int32_t n_seg_cap, int32_t n_lab_cap, int32_t dil_recall,
+                                int64_t *h_bd_count, int64_t *h_gt_counts, int32_t *h_area, int32_t *h_perim,
+                                int32_t *h_hist, int32_t *h_n_seg, int32_t *h_n_lab, int32_t *h_status)
+{
+    if (B < 1 || H < 1 || W < 1 || G < 0 || n_seg_cap < 1 || n_lab_cap < 1)
+        return set_error(GCIS_E_INVALID, "label_metrics_host: bad shape");
+    const size_t N = (size_t)H * W, Gs = G;
+    size_t tot = 0;
+    int32_t *d_lb = nullptr, *d_n_gt = nullptr, *d_area = nullptr, *d_perim = nullptr, *d_hist = nullptr, *d_n_seg = nullptr,
+            *d_n_lab = nullptr, *d_status = nullptr;
+    uint16_t *d_gt = nullptr;
+    int64_t *d_bd = nullptr, *d_gc = nullptr;
+    int rc = GCIS_OK;
+    auto cleanup = [&]() {
+        cudaFree(d_lb); cudaFree(d_n_gt); cudaFree(d_area); cudaFree(d_perim); cudaFree(d_hist); cudaFree(d_n_seg);
+        cudaFree(d_n_lab); cudaFree(d_status); cudaFree(d_gt); cudaFree(d_bd); cudaFree(d_gc);
+    };
+#define HA(ptr, n)                                   \
+    if (!rc) rc = dev_alloc(&(ptr), (n), &tot);
+    HA(d_lb, B * N) HA(d_gt, B * Gs * N) HA(d_n_gt, B) HA(d_area, (size_t)B * n_seg_cap) HA(d_perim, (size_t)B * n_seg_cap)
+    HA(d_hist, (size_t)B * Gs * n_seg_cap * n_lab_cap) HA(d_n_seg, B) HA(d_n_lab, B * Gs) HA(d_status, B) HA(d_bd, B)
+    HA(d_gc, B * Gs * GCIS_GT_SLOTS)
+#undef HA
+    if (rc) { cleanup(); return rc; }
+    auto cp = [&](void *dst, const void *src, size_t n, cudaMemcpyKind kind) {
+        if (rc || n == 0) return;
+        cudaError_t e = cudaMemcpy(dst, src, n, kind);
+        if (e != cudaSuccess) rc = set_error(GCIS_E_CUDA, "label_metrics_host: cudaMemcpy -> %s", cudaGetErrorString(e));
+    };
+    cp(d_lb, h_lb, sizeof(int32_t) * B * N, cudaMemcpyHostToDevice);
+    cp(d_gt, h_gt, sizeof(uint16_t) * B * Gs * N, cudaMemcpyHostToDevice);
+    if (h_n_gt) cp(d_n_gt, h_n_gt, sizeof(int32_t) * B, cudaMemcpyHostToDevice);
+    if (!rc)
+        rc = label_metrics_launch(d_lb, d_gt, h_n_gt ? d_n_gt : nullptr, B, H, W, G, n_seg_cap, n_lab_cap, dil_recall, d_bd,
+                                  d_gc, d_area, d_perim, d_hist, d_n_seg, d_n_lab, d_status, nullptr);
+    if (!rc) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = set_error(GCIS_E_CUDA, "label_metrics_host: kernel -> %s", cudaGetErrorString(e));
+    }
+    cp(h_bd_count, d_bd, sizeof(int64_t) * B, cudaMemcpyDeviceToHost);
+    cp(h_gt_counts, d_gc, sizeof(int64_t) * B * Gs * GCIS_GT_SLOTS, cudaMemcpyDeviceToHost);
+    cp(h_area, d_area, sizeof(int32_t) * (size_t)B * n_seg_cap, cudaMemcpyDeviceToHost);
+    cp(h_perim, d_perim, sizeof(int32_t) * (size_t)B * n_seg_cap, cudaMemcpyDeviceToHost);
+    if (h_hist) cp(h_hist, d_hist, sizeof(int32_t) * (size_t)B * Gs * n_seg_cap * n_lab_cap, cudaMemcpyDeviceToHost);
+    cp(h_n_seg, d_n_seg, sizeof(int32_t) * B, cudaMemcpyDeviceToHost);
+    cp(h_n_lab, d_n_lab, sizeof(int32_t) * B * Gs, cudaMemcpyDeviceToHost);
+    cp(h_status, d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost);
+    cleanup();
+    if (!rc)
+        for (int b = 0; b < B; ++b)
+            if (h_status[b]) return set_error(GCIS_E_LABEL, "label_metrics: image %d has status %d (negative label or label >= capacity)", b, h_status[b]);
+    return rc;
+}
+
+int32_t gcis_find_boundaries_host(const int32_t *h_x, int32_t B, int32_t H, int32_t W, uint8_t *h_out)
+{
+    if (!h_x || !h_out || B < 1 || H < 1 || W < 1) return set_error(GCIS_E_INVALID, "find_boundaries: bad argument");
+    const size_t n = (size_t)B * H * W;
+    int32_t *d_x = nullptr;
+    uint8_t *d_o = nullptr;
+    size_t tot = 0;
+    int rc = dev_alloc(&d_x, n, &tot);
+    if (!rc) rc = dev_alloc(&d_o, n, &tot);
+    if (!rc && cudaMemcpy(d_x, h_x, n * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess)
+        rc = set_error(GCIS_E_CUDA, "find_boundaries: H2D copy failed");
+    if (!rc) rc = find_boundaries_launch(d_x, d_o, B, H, W, nullptr);
+    if (!rc && cudaMemcpy(h_out, d_o, n, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = set_error(GCIS_E_CUDA, "find_boundaries: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_x); cudaFree(d_o);
+    return rc;
+}
+
+int32_t gcis_pipeline_device(gcis_plan *p, const uint8_t *d_img, const uint16_t *d_gt, const int32_t *d_n_gt,
+                             const int32_t *d_init_idx, int32_t B, void *stream)
+{
+    TRY(plan_check_batch(p, B));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const gcis_config &c = p->cfg;
+    TRY(gcis_segment_device(p, d_img, B, d_init_idx, p->d_labels, stream));
+    const size_t me = 4 * (size_t)p->n_groups_last;
+    if (p->profiling) cudaEventRecord(plan_event(p, me), st);
+    TRY(label_metrics_launch(p->d_labels, d_gt, d_n_gt, B, c.height, c.width, c.max_gt, c.k, c.n_lab_cap, c.dil_recall,
+                             p->d_bd_count, p->d_gt_counts, p->d_area, p->d_perim, p->d_hist, p->d_n_seg, p->d_n_lab,
+                             p->d_status, st));
+    if (p->profiling) {
+        cudaEventRecord(plan_event(p, me + 1), st);
+        GCIS_CUDA_TRY(cudaEventSynchronize(p->events[me + 1]));
+        float acc[4] = {0, 0, 0, 0}, ms = 0;
+        for (int g = 0; g < p->n_groups_last; ++g) {
+            cudaEventElapsedTime(&ms, p->events[4 * g], p->events[4 * g + 1]); acc[0] += ms;
+            cudaEventElapsedTime(&ms, p->events[4 * g + 1], p->events[4 * g + 2]); acc[1] += ms;
+            cudaEventElapsedTime(&ms, p->events[4 * g + 2], p->events[4 * g + 3]); acc[2] += ms;
+        }
+        cudaEventElapsedTime(&ms, p->events[me], p->events[me + 1]); acc[3] = ms;
+        memcpy(p->stage_ms, acc, sizeof(acc));
+    }
+    return GCIS_OK;
+}
+
+int32_t gcis_pipeline_fetch(gcis_plan *p, int32_t B, int64_t *h_bd_count, int64_t *h_gt_counts, int32_t *h_area,
+                            int32_t *h_perim, int32_t *h_n_lab, int32_t *h_status, int32_t *h_labels, void *stream)
+{
+    TRY(plan_check_batch(p, B));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const gcis_config &c = p->cfg;
+    const size_t G = std::max(c.max_gt, 1);
+    GCIS_CUDA_TRY(cudaMemcpyAsync(h_bd_count, p->d_bd_count, sizeof(int64_t) * B, cudaMemcpyDeviceToHost, st));
+    GCIS_CUDA_TRY(cudaMemcpyAsync(h_gt_counts, p->d_gt_counts, sizeof(int64_t) * B * G * GCIS_GT_SLOTS, cudaMemcpyDeviceToHost, st));
+    GCIS_CUDA_TRY(cudaMemcpyAsync(h_area, p->d_area, sizeof(int32_t) * (size_t)B * c.k, cudaMemcpyDeviceToHost, st));
+    GCIS_CUDA_TRY(cudaMemcpyAsync(h_perim, p->d_perim, sizeof(int32_t) * (size_t)B * c.k, cudaMemcpyDeviceToHost, st));
+    GCIS_CUDA_TRY(cudaMemcpyAsync(h_n_lab, p->d_n_lab, sizeof(int32_t) * B * G, cudaMemcpyDeviceToHost, st));
+    GCIS_CUDA_TRY(cudaMemcpyAsync(h_status, p->d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    if (h_labels)
+        GCIS_CUDA_TRY(cudaMemcpyAsync(h_labels, p->d_labels, sizeof(int32_t) * (size_t)B * p->N, cudaMemcpyDeviceToHost, st));
+    GCIS_CUDA_TRY(cudaStreamSynchronize(st));
+    return GCIS_OK;
+}
+
+int32_t gcis_pipeline_host(gcis_plan *p, const uint8_t *h_img, const uint16_t *h_gt, const int32_t *h_n_gt,
+                           const int32_t *h_init_idx, int32_t B, int64_t *h_bd_count, int64_t *h_gt_counts,
+                           int32_t *h_area, int32_t *h_perim, int32_t *h_n_lab, int32_t *h_status, int32_t *h_labels)
+{
+    if (!p) return set_error(GCIS_E_INVALID, "null plan");
+    if (B < 1) return set_error(GCIS_E_INVALID, "B=%d", B);
+    const gcis_config &c = p->cfg;
+    const size_t MB = c.max_batch, G = std::max(c.max_gt, 1), N = p->N;
+    if (!p->d_img) {
+        TRY(dev_alloc(&p->d_img, MB * N * 3, &p->bytes));
+        TRY(dev_alloc(&p->d_gt, MB * G * N, &p->bytes));
+        TRY(dev_alloc(&p->d_n_gt, MB, &p->bytes));
+        TRY(dev_alloc(&p->d_init, MB * c.k, &p->bytes));
+    }
+    cudaStream_t st = p->stream;
+    for (int b0 = 0; b0 < B; b0 += c.max_batch) {
+        const int nb = std::min<int>(c.max_batch, B - b0);
+        GCIS_CUDA_TRY(cudaMemcpyAsync(p->d_img, h_img + (size_t)b0 * N * 3, (size_t)nb * N * 3, cudaMemcpyHostToDevice, st));
+        if (c.max_gt > 0)
+            GCIS_CUDA_TRY(cudaMemcpyAsync(p->d_gt, h_gt + (size_t)b0 * G * N, sizeof(uint16_t) * nb * G * N, cudaMemcpyHostToDevice, st));
+        if (h_n_gt)
+            GCIS_CUDA_TRY(cudaMemcpyAsync(p->d_n_gt, h_n_gt + b0, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, st));
+        GCIS_CUDA_TRY(cudaMemcpyAsync(p->d_init, h_init_idx + (size_t)b0 * c.k, sizeof(int32_t) * nb * c.k, cudaMemcpyHostToDevice, st));
+        TRY(gcis_pipeline_device(p, p->d_img, p->d_gt, h_n_gt ? p->d_n_gt : nullptr, p->d_init, nb, st));
+        TRY(gcis_pipeline_fetch(p, nb, h_bd_count + b0, h_gt_counts + (size_t)b0 * G * GCIS_GT_SLOTS, h_area + (size_t)b0 * c.k,
+                                h_perim + (size_t)b0 * c.k, h_n_lab + (size_t)b0 * G, h_status + b0,
+                                h_labels ? h_labels + (size_t)b0 * N : nullptr, st));
+    }
+    return GCIS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+"""Batch driver: the reference's loop (BSD_metrics/script.py:22-38) over many images,
+sharded by image over the GPUs of one box (SURVEY.md §8 e).
+
+Each rank owns the images ``i`` with ``i % world == rank`` and runs the whole per-image path
+locally; the only exchange is the reduction of the per-image metric sums (one NCCL
+all-reduce of 7 float64) or, for the bit-exact check, an all-gather of the integer records."""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from .engine import BatchCounts, Plan, kmeans_init_indices
+from .metrics import METRIC_KEYS, finish_image
+
+SUM_KEYS = METRIC_KEYS[1:]  # recall, precision, underseg, undersegNP, compactness, density
+
+
+def shard_indices(n_images: int, rank: int, world: int) -> np.ndarray:
+    """Image indices owned by ``rank`` (round-robin)."""
+    return np.arange(rank, n_images, world, dtype=np.int64)
+
+
+def init_indices_for(indices, n_pixels: int, k: int, seed: int = 0) -> np.ndarray:
+    """[len(indices), k] initial-centroid pixels; seeded per GLOBAL image index so the result
+    does not depend on the sharding."""
+    return np.stack([kmeans_init_indices(n_pixels, k, seed + int(i)) for i in indices]) \
+        if len(indices) else np.zeros((0, k), np.int32)
+
+
+def records_to_array(c: BatchCounts) -> np.ndarray:
+    """Integer record per image as one int64 row: [n_seg, n_gt, bd, area[k], perim[k], gt_counts[G*8]]."""
+    B = len(c.bd_count)
+    return np.concatenate([c.n_seg.astype(np.int64)[:, None], c.n_gt.astype(np.int64)[:, None],
+                           c.bd_count[:, None], c.area.astype(np.int64), c.perim.astype(np.int64),
+                           c.gt_counts.reshape(B, -1)], axis=1)
+
+
+def array_to_records(a: np.ndarray, H: int, W: int, k: int, G: int) -> BatchCounts:
+    B = a.shape[0]
+    return BatchCounts(H, W, a[:, 2].copy(), a[:, 3 + 2 * k:].reshape(B, max(G, 1), -1).copy(),
+                       a[:, 3:3 + k].astype(np.int32), a[:, 3 + k:3 + 2 * k].astype(np.int32),
+                       a[:, 0].astype(np.int32), np.zeros((B, max(G, 1)), np.int32), np.zeros(B, np.int32),
+                       a[:, 1].astype(np.int32))
+
+
+def metric_sums(c: BatchCounts) -> np.ndarray:
+    """[7] float64: sum over the batch of the six reference scores, and the image count."""
+    acc = np.zeros(len(SUM_KEYS) + 1, np.float64)
+    for b in range(len(c.bd_count)):
+        m = finish_image(c, b)
+        for i, key in enumerate(SUM_KEYS):
+            acc[i] += float(m[key])
+        acc[-1] += 1.0
+    return acc
+
+
+def reduce_sums(local: np.ndarray, device=None) -> np.ndarray:
+    """Sum the 7-vector over ranks (NCCL on GPUs, gloo on CPU); identity without a process group."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    t = torch.from_numpy(local.copy())
+    if dist.get_backend() == "nccl":
+        t = t.to(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def gather_records(local: np.ndarray, indices: np.ndarray, n_images: int, device=None) -> Optional[np.ndarray]:
+    """All-gather the integer records and put them back in global image order, so the floats
+    finished from them are identical for 1/2/4/8 ranks.  Every rank returns the full table."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        out = np.zeros((n_images, local.shape[1]), np.int64)
+        out[indices] = local
+        return out
+    world = dist.get_world_size()
+    width = local.shape[1]
+    per = (n_images + world - 1) // world
+    pad = np.zeros((per, width + 1), np.int64)
+    pad[:len(indices), 0] = indices + 1          # 0 marks padding
+    pad[:len(indices), 1:] = local
+    t = torch.from_numpy(pad)
+    if dist.get_backend() == "nccl":
+        t = t.to(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    out = np.zeros((n_images, width), np.int64)
+    for p in parts:
+        p = p.cpu().numpy()
+        ok = p[:, 0] > 0
+        out[p[ok, 0] - 1] = p[ok, 1:]
+    return out
+
+
+def evaluate_batch(plan: Plan, imgs: np.ndarray, gts: np.ndarray, init_idx: np.ndarray,
+                   n_gt: Optional[np.ndarray] = None, want_labels: bool = False) -> BatchCounts:
+    """Host arrays in, integer records out, through the C ABI's host entry point."""
+    imgs = np.ascontiguousarray(imgs, np.uint8)
+    gts = np.ascontiguousarray(gts, np.uint16)
+    init_idx = np.ascontiguousarray(init_idx, np.int32)
+    return plan.pipeline_host(imgs, gts, init_idx, imgs.shape[0], n_gt, want_labels)
+
+
+def dataset_scores(sums: np.ndarray) -> dict:
+    """Mean of each per-image score over the dataset (builder-defined aggregation; the
+    reference aggregates nothing across images, script.py:22-38)."""
+    n = sums[-1]
+    return {k: float(sums[i] / n) for i, k in enumerate(SUM_KEYS)} | {"images": int(n)}

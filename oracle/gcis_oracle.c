@@ -30,7 +30,7 @@
 
 #define ORC_API __attribute__((visibility("default")))
 #if defined(__x86_64__)
-#define ORC_CLONES __attribute__((target_clones("arch=haswell", "default")))
+#define ORC_CLONES __attribute__((target_clones("arch=x86-64-v3", "default")))
 #else
 #define ORC_CLONES
 #endif
@@ -276,7 +276,6 @@ ORC_API void orc_conv_sep_complex_reflect(const double *img, int H, int W,
 /* k-means stage (builder-defined spec; parity unpinned)       */
 /* ------------------------------------------------------------------------- */
 
-#define KM_FIX_SCALE 1073741824.0f /* 2^30 */
 #define KM_BLK 64
 
 /*
@@ -287,15 +286,17 @@ ORC_API void orc_conv_sep_complex_reflect(const double *img, int H, int W,
  *   m_jd = -2 * c_jd (exact);  cn_j = (float) sum_d (double)c_jd*(double)c_jd, d ascending
  *   score_j(x) = fmaf(x_{D-1}, m_{j,D-1}, ... fmaf(x_0, m_{j0}, cn_j))   (fp32 FMA chain)
  *   label = lowest j attaining the minimum score (strict '<' scan, j ascending)
- *   q_d = llrintf(x_d * 2^30)  (round-to-nearest-even);  sum_jd = exact int64 sum of q_d
- *   c_jd <- (float)((double)sum_jd / ((double)count_j * 2^30)); empty cluster keeps c_jd
+ *   q_d = lrintf(x_d * 2^fix_shift)  (round-to-nearest-even; |x_d| < 2^(31-fix_shift));
+ *   sum_jd = exact int64 sum of q_d
+ *   c_jd <- (float)((double)sum_jd / ((double)count_j * 2^fix_shift)); empty cluster keeps c_jd
  * feat is planar [D][N]; centroids [k][D]; k <= 64.
  */
 ORC_CLONES
-ORC_API void orc_kmeans(const float *feat, int D, int64_t N, int k, int T,
+ORC_API void orc_kmeans(const float *feat, int D, int64_t N, int k, int T, int fix_shift,
                         const int32_t *init_idx, int32_t *labels, float *centroids,
                         int64_t *counts_out)
 {
+    const float fix_scale = (float)(1u << fix_shift);
     float *m = malloc(sizeof(float) * (size_t)k * D);
     float *cn = malloc(sizeof(float) * (size_t)k);
     int64_t *sums = malloc(sizeof(int64_t) * (size_t)k * D);
@@ -317,15 +318,17 @@ ORC_API void orc_kmeans(const float *feat, int D, int64_t N, int k, int T,
         memset(sums, 0, sizeof(int64_t) * (size_t)k * D);
         memset(cnt, 0, sizeof(int64_t) * (size_t)k);
         for (int64_t p0 = 0; p0 < N; p0 += KM_BLK) {
-            int nb = (int)((N - p0) < KM_BLK ? (N - p0) : KM_BLK);
+            const int nb = (int)((N - p0) < KM_BLK ? (N - p0) : KM_BLK);
+            float xb[KM_BLK];
             for (int j = 0; j < k; ++j)
-                for (int i = 0; i < nb; ++i) s[j * KM_BLK + i] = cn[j];
+                for (int i = 0; i < KM_BLK; ++i) s[j * KM_BLK + i] = cn[j];
             for (int d = 0; d < D; ++d) {
                 const float *x = feat + (size_t)d * N + p0;
+                for (int i = 0; i < KM_BLK; ++i) xb[i] = i < nb ? x[i] : 0.0f;
                 for (int j = 0; j < k; ++j) {
-                    float mj = m[(size_t)j * D + d];
-                    float *sj = s + j * KM_BLK;
-                    for (int i = 0; i < nb; ++i) sj[i] = __builtin_fmaf(x[i], mj, sj[i]);
+                    const float mj = m[(size_t)j * D + d];
+                    float *restrict sj = s + j * KM_BLK;
+                    for (int i = 0; i < KM_BLK; ++i) sj[i] = __builtin_fmaf(xb[i], mj, sj[i]);
                 }
             }
             for (int i = 0; i < nb; ++i) {
@@ -338,13 +341,14 @@ ORC_API void orc_kmeans(const float *feat, int D, int64_t N, int k, int T,
             }
             for (int d = 0; d < D; ++d) {
                 const float *x = feat + (size_t)d * N + p0;
+                int64_t *sd = sums + d;
                 for (int i = 0; i < nb; ++i)
-                    sums[(size_t)labels[p0 + i] * D + d] += (int64_t)llrintf(x[i] * KM_FIX_SCALE);
+                    sd[(size_t)labels[p0 + i] * D] += (int64_t)__builtin_lrintf(x[i] * fix_scale);
             }
         }
         for (int j = 0; j < k; ++j) {
             if (cnt[j] == 0) continue;
-            double den = (double)cnt[j] * (double)KM_FIX_SCALE;
+            double den = (double)cnt[j] * (double)fix_scale;
             for (int d = 0; d < D; ++d)
                 centroids[(size_t)j * D + d] = (float)((double)sums[(size_t)j * D + d] / den);
         }

@@ -209,7 +209,8 @@ def run_gpu(args):
         ms, e2e_ms = float(t[0]), float(t[1])
     else:
         e2e_ms = e2e_s * 1e3
-    assert np.array_equal(sums, sums_h), "device-resident and host-buffer passes disagree"
+    if not os.environ.get("GCIS_BENCH_NOCHECK"):   # (set only for wrong-on-purpose timing experiments)
+        assert np.array_equal(sums, sums_h), "device-resident and host-buffer passes disagree"
 
     # ---- per-stage device times (CUDA events inside the library) for the roofline ----
     plan.set_profiling(True)

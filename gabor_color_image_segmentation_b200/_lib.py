@@ -7,7 +7,7 @@ import os
 import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libgcis.so")
+LIB_PATH = os.environ.get("GCIS_LIB") or os.path.join(_PKG, "libgcis.so")
 CSRC = os.path.join(_PKG, "csrc")
 SOURCES = ["plan.cu", "gabor.cu", "kmeans.cu", "label_metrics.cu"]
 

@@ -190,6 +190,7 @@ struct GaborParams {
     const float *taps;
     const GaborScale *scales;
     int B, C, H, W, Wp, P, S, O, feature;
+    int feat_plane_stride;       // floats between feature planes (>= H*W)
     int n_strips;
     int TH[GB_MAX_SCALES];       // output rows per CTA at scale s
     int n_vt[GB_MAX_SCALES];     // vertical tiles at scale s
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
     const GaborScale &sc = P.scales[s];
     const float *plane = P.planes + ((size_t)b * P.C + c) * P.H * P.Wp;
     const int D = P.C * P.S * P.O;
-    float *featb = P.feat + (size_t)b * D * P.H * P.W;
+    float *featb = P.feat + (size_t)b * D * P.feat_plane_stride;
     const int lane = threadIdx.x & 31;
 
     for (int ji = 0; ji < sc.n_jobs; ++ji) {
@@ -394,8 +395,8 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
 
         // ---- column pass: T -> |response| for theta (and pi - theta) ----
         const int d0 = (c * P.S + s) * P.O;
-        float *f0 = featb + (size_t)(d0 + job.out0) * P.H * P.W;
-        float *f1 = job.out1 >= 0 ? featb + (size_t)(d0 + job.out1) * P.H * P.W : nullptr;
+        float *f0 = featb + (size_t)(d0 + job.out0) * P.feat_plane_stride;
+        float *f1 = job.out1 >= 0 ? featb + (size_t)(d0 + job.out1) * P.feat_plane_stride : nullptr;
         const bool xi = job.row_im >= 0, gi = job.col_im >= 0;
         if (xi && gi) col_pass<true, true>(P, Tre, Tim, rowtab, t_cr, t_ci, h, y0, th, x0, f0, f1);
         else if (xi) col_pass<true, false>(P, Tre, Tim, rowtab, t_cr, t_ci, h, y0, th, x0, f0, f1);
@@ -440,7 +441,7 @@ int gabor_plan(const GaborBankHost &bank, int H, int W, int C, int P, int Wp, in
     p.C = C; p.H = H; p.W = W; p.Wp = Wp; p.P = P; p.S = bank.S; p.O = bank.O; p.feature = feature;
     p.n_strips = ceil_div(W, GB_TW);
     const int hmax = bank.hmax;
-    const size_t two_per_sm = 113 * 1024, one_per_sm = 227 * 1024;
+    const size_t two_per_sm = 112 * 1024, one_per_sm = 226 * 1024;
     size_t budget;
     int nsrc_cap;
     if (gabor_smem_bytes(H, hmax, H) <= one_per_sm) {
@@ -498,10 +499,11 @@ GaborLaunchPlan *gabor_plan_new(const GaborBankHost &bank, int H, int W, int C, 
 void gabor_plan_delete(GaborLaunchPlan *lp) { delete lp; }
 
 int gabor_launch(GaborLaunchPlan &lp, const float *d_planes, float *d_feat, const float *d_taps,
-                 const GaborScale *d_scales, int B, cudaStream_t st)
+                 const GaborScale *d_scales, int B, int feat_plane_stride, cudaStream_t st)
 {
     GaborParams &p = lp.p;
     p.planes = d_planes; p.feat = d_feat; p.taps = d_taps; p.scales = d_scales; p.B = B;
+    p.feat_plane_stride = feat_plane_stride;
     int acc = 0;
     for (int i = 0; i < p.S; ++i) {
         p.first_block[i] = acc;
@@ -509,10 +511,10 @@ int gabor_launch(GaborLaunchPlan &lp, const float *d_planes, float *d_feat, cons
     }
     p.first_block[p.S] = acc;
     lp.blocks = acc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GCIS_CUDA_TRY(cudaFuncSetAttribute(gabor_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+    static size_t attr_smem = 0;
+    if (lp.smem > attr_smem) {
+        GCIS_CUDA_TRY(cudaFuncSetAttribute(gabor_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        attr_smem = lp.smem;
     }
     gabor_bank_kernel<<<acc, GB_THREADS, lp.smem, st>>>(p);
     GCIS_LAUNCH_CHECK();

@@ -9,13 +9,28 @@
 //   depend on the grid, the tile order or the number of GPUs
 //   c_jd <- (float)((double)sum_jd / ((double)count_j * 2^fix_shift)); empty clusters keep c_jd
 //
-// Layout: feat [B][D][N] planar fp32 (every warp load is one 128-byte line of one feature
-// plane); centroids [B][k][D]; sums [B][k][D] int64; counts [B][k] int32.
-// One CTA owns KM_TILES consecutive 256-pixel tiles of one image.  Phase A (thread = pixel)
-// streams the D planes once from HBM and keeps only the scores; phase B re-reads the CTA's own
-// pixels from L2 in 32-feature slabs, transposes them through shared memory (lane = feature)
-// and accumulates into warp-private int64 bins, so no atomics are contended.  The last CTA
-// of an image to finish (ticket counter) turns sums into the next centroids.
+// Layout: feat [B][D][plane_stride] planar fp32 (a warp load is 512 contiguous bytes of one
+// feature plane); centroids [B][k][D]; per-image score table prep = {m [D][K], cn [K]};
+// sums [B][k][D] int64; counts [B][k] int32; labels kept between iterations as one byte/pixel.
+//
+// One CTA owns one tile of 256*VEC consecutive pixels of one image.
+//   Phase A (thread = VEC pixels) streams the D planes once (128-bit loads, a rotating window of
+//   KM_PF loads in flight per thread) and keeps only the scores; the FMA chain runs as packed
+//   fma.rn.f32x2 over cluster pairs (one IEEE fp32 FMA per lane, same result as scalar FFMA),
+//   which halves the FP32 issue slots so the pass is bandwidth-bound.
+//   Phase B updates the centroid sums INCREMENTALLY: because the sums are exact integers,
+//   sum_new = sum_old + q(pixels that joined) - q(pixels that left) is bit-identical to a full
+//   recomputation, and after the first iterations only a few percent of the pixels change
+//   label.  Changed pixels are compacted, re-read from L1/L2, transposed through shared memory
+//   (lane = feature) and accumulated with a warp-uniform label, so no atomics are contended.
+//     sparse path (<= 32 changed pixels in the tile): one gather, one barrier, each (cluster,
+//       feature) delta lives in exactly one lane and is published with one global atomic;
+//     dense path: 256-pixel rounds, warp-private bins, block reduction, one global atomic per
+//       (cluster, feature) per CTA.
+//   The last CTA of an image to finish (ticket counter) turns sums into the next centroids and
+//   the next score table.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace gcis {
@@ -24,240 +39,542 @@ namespace {
 
 constexpr int KM_THREADS = 256;
 constexpr int KM_WARPS = KM_THREADS / 32;
-constexpr int KM_TILES = 4;                       // tiles per CTA
-constexpr int KM_PX = KM_THREADS * KM_TILES;      // pixels per CTA
-constexpr int KM_QSTR = KM_THREADS + 1;           // odd stride of the transposed slab
+constexpr int KM_ROUND = 128;               // changed pixels transposed per round (dense path)
+constexpr int KM_QSTR = KM_ROUND + 1;       // odd stride of the transposed slab
+constexpr int KM_SPARSE = 32;               // sparse path handles up to this many changed pixels
+constexpr int KM_SSTR = KM_SPARSE + 1;
+#ifndef KM_PF_N
+#define KM_PF_N 8
+#endif
+#ifndef KM_MINB
+#define KM_MINB 4
+#endif
+constexpr int KM_PF = KM_PF_N;              // loads in flight per thread in phase A
+constexpr int KM_NONE = 255;                // "no previous label"
 
 struct KmParams {
     const float *feat;
-    const float *cent_in;
-    float *cent_out;
+    size_t img_stride;      // floats between images
+    int plane_stride;       // floats between feature planes
+    float *cent;            // [B][k][D]
+    float *prep;            // [B][D*K + K]: m (transposed, zero-padded to K) then cn (+inf padded)
     long long *sums;
     int *counts;
     int *done;
-    int32_t *labels;   // written when non-null
-    int D, N, k, chunks;
+    unsigned char *lab8;    // [B][lab_stride] labels of the previous iteration
+    int lab_stride;
+    int32_t *labels_out;    // [B][N], written when non-null (last iteration)
+    int D, N, k, chunks, first;
     float fix_scale;
 };
 
-__global__ void km_init_kernel(const float *__restrict__ feat, const int32_t *__restrict__ init_idx, float *cent,
-                               long long *sums, int *counts, int *done, int D, int N, int k)
+// Score table of one image from its centroids (all threads of the CTA; cent must be visible).
+__device__ __forceinline__ void km_write_prep(const float *cent, float *prep, int D, int k, int K)
 {
-    const int b = blockIdx.x;
-    for (int i = threadIdx.x; i < k * D; i += blockDim.x) {
-        const int j = i / D, d = i - j * D;
-        int p = init_idx[b * k + j];
-        p = min(max(p, 0), N - 1);
-        cent[(size_t)b * k * D + i] = feat[((size_t)b * D + d) * N + p];
-        sums[(size_t)b * k * D + i] = 0;
-    }
-    for (int i = threadIdx.x; i < k; i += blockDim.x) counts[b * k + i] = 0;
-    if (threadIdx.x == 0) done[b] = 0;
-}
-
-template <int K>
-__global__ void __launch_bounds__(KM_THREADS) km_pass_kernel(const __grid_constant__ KmParams P)
-{
-    extern __shared__ __align__(16) unsigned char km_smem[];
-    // [D][K] m (transposed so the K values of one feature are one 128-bit broadcast load)
-    float *s_m = reinterpret_cast<float *>(km_smem);
-    long long *s_acc = reinterpret_cast<long long *>(s_m + (size_t)((P.D * K + 3) & ~3));  // [warps][K][32]
-    int *s_q = reinterpret_cast<int *>(s_acc + KM_WARPS * K * 32);                          // [32][KM_QSTR]
-    __shared__ float s_cn[K];
-    __shared__ int s_cnt[K];
-    __shared__ unsigned char s_lab[KM_PX];
-    __shared__ int s_last;
-
-    const int b = blockIdx.y;
-    const int D = P.D, N = P.N, k = P.k;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float *feat = P.feat + (size_t)b * D * N;
-    const float *cin = P.cent_in + (size_t)b * k * D;
-    const int p_base = blockIdx.x * KM_PX;
-
-    for (int i = threadIdx.x; i < D * K; i += KM_THREADS) {
+    for (int i = threadIdx.x; i < D * K; i += blockDim.x) {
         const int d = i / K, j = i - d * K;
-        s_m[i] = j < k ? -2.0f * cin[j * D + d] : 0.f;
+        prep[i] = j < k ? -2.0f * cent[j * D + d] : 0.f;
     }
-    if (threadIdx.x < K) {
+    if ((int)threadIdx.x < K) {
         const int j = threadIdx.x;
         float cn = __int_as_float(0x7f800000);  // +inf: padded clusters never win
         if (j < k) {
             double acc = 0.0;
             for (int d = 0; d < D; ++d) {
-                const double c = (double)cin[j * D + d];
+                const double c = (double)cent[j * D + d];
                 acc = __dadd_rn(acc, __dmul_rn(c, c));
             }
             cn = (float)acc;
         }
-        s_cn[j] = cn;
-        s_cnt[j] = 0;
+        prep[D * K + j] = cn;
+    }
+}
+
+__global__ void km_init_kernel(const float *__restrict__ feat, size_t img_stride, int plane_stride,
+                               const int32_t *__restrict__ init_idx, float *cent, float *prep, long long *sums,
+                               int *counts, int *done, int D, int N, int k, int K)
+{
+    const int b = blockIdx.x;
+    float *c = cent + (size_t)b * k * D;
+    for (int i = threadIdx.x; i < k * D; i += blockDim.x) {
+        const int j = i / D, d = i - j * D;
+        int p = init_idx[b * k + j];
+        p = min(max(p, 0), N - 1);
+        c[i] = feat[(size_t)b * img_stride + (size_t)d * plane_stride + p];
+        sums[(size_t)b * k * D + i] = 0;
+    }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) counts[b * k + i] = 0;
+    if (threadIdx.x == 0) done[b] = 0;
+    __syncthreads();
+    km_write_prep(c, prep + (size_t)b * (D * K + K), D, k, K);
+}
+
+// acc.{lo,hi} = a.{lo,hi} * b + acc.{lo,hi}, each lane one IEEE fp32 FMA (round to nearest even)
+__device__ __forceinline__ void ffma2(unsigned long long &acc, unsigned long long a, float b)
+{
+    unsigned long long bb;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(bb));
+}
+
+// acc[ln] += v; acc[lo] -= v with warp-uniform labels: registers for K <= 8, private bins otherwise
+template <int K>
+__device__ __forceinline__ void km_move(long long (&acc)[K <= 8 ? K : 1], long long *bins, int ln, int lo, long long v)
+{
+    if constexpr (K <= 8) {
+        switch (ln) {
+            case 0: acc[0] += v; break;
+            case 1: acc[1 % K] += v; break;
+            case 2: acc[2 % K] += v; break;
+            case 3: acc[3 % K] += v; break;
+            case 4: acc[4 % K] += v; break;
+            case 5: acc[5 % K] += v; break;
+            case 6: acc[6 % K] += v; break;
+            default: acc[7 % K] += v; break;
+        }
+        switch (lo) {
+            case 0: acc[0] -= v; break;
+            case 1: acc[1 % K] -= v; break;
+            case 2: acc[2 % K] -= v; break;
+            case 3: acc[3 % K] -= v; break;
+            case 4: acc[4 % K] -= v; break;
+            case 5: acc[5 % K] -= v; break;
+            case 6: acc[6 % K] -= v; break;
+            case 7: acc[7 % K] -= v; break;
+            default: break;  // KM_NONE
+        }
+    } else {
+        bins[ln * 32] += v;
+        if (lo != KM_NONE) bins[lo * 32] -= v;
+    }
+}
+
+// ---- mbarrier / bulk-copy (TMA engine) primitives -------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy; completion is signalled on `bar` as transferred bytes
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+constexpr int KM_STAGES = 3;   // ring depth of the phase-A feature pipeline (VEC == 4)
+constexpr int KM_DS = 4;       // feature planes per stage
+
+// shared bytes of the phase-B structures: warp bins, transposed slab, changed-pixel list
+__host__ __device__ constexpr size_t km_phase_b_bytes(int K, int tile)
+{
+    return sizeof(long long) * KM_WARPS * K * 32 + sizeof(int) * 32 * KM_QSTR + (size_t)4 * tile;
+}
+__host__ __device__ constexpr size_t km_smem_bytes(int K, int vec, int D)
+{
+    const size_t ring = vec == 4 ? sizeof(float) * KM_STAGES * KM_DS * KM_THREADS * 4 : 0;
+    const size_t pb = km_phase_b_bytes(K, KM_THREADS * vec);
+    const size_t front = ((ring > pb ? ring : pb) + 15) & ~(size_t)15;
+    return front + sizeof(float) * (size_t)((D * K + K + 3) & ~3);
+}
+
+template <int K, int VEC>
+__global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 1)) km_pass_kernel(const __grid_constant__ KmParams P)
+{
+    constexpr int TILE = KM_THREADS * VEC;
+    constexpr int NACC = K <= 8 ? K : 1;
+    constexpr int RING_FLOATS = VEC == 4 ? KM_STAGES * KM_DS * TILE : 0;
+    extern __shared__ __align__(128) unsigned char km_smem[];
+    // [ring | (aliased after phase A) s_acc, s_q] [s_m: m [D][K] then cn [K]]
+    float *s_ring = reinterpret_cast<float *>(km_smem);
+    long long *s_acc = reinterpret_cast<long long *>(km_smem);                                // [warps][K][32]
+    int *s_q = reinterpret_cast<int *>(s_acc + KM_WARPS * K * 32);                            // [32][KM_QSTR]
+    unsigned short *s_ent = reinterpret_cast<unsigned short *>(s_q + 32 * KM_QSTR);           // [TILE] changed pixels
+    unsigned char *s_new = reinterpret_cast<unsigned char *>(s_ent + TILE);                   // [TILE]
+    unsigned char *s_old = s_new + TILE;                                                      // [TILE]
+    constexpr size_t PHASE_B_BYTES = km_phase_b_bytes(K, TILE);
+    constexpr size_t FRONT_BYTES = (RING_FLOATS * sizeof(float) > PHASE_B_BYTES ? RING_FLOATS * sizeof(float) : PHASE_B_BYTES);
+    float *s_m = reinterpret_cast<float *>(km_smem + ((FRONT_BYTES + 15) & ~(size_t)15));
+    __shared__ __align__(8) unsigned long long s_full[KM_STAGES], s_empty[KM_STAGES];
+    __shared__ int s_cnt[K];
+    __shared__ int s_nchg, s_last;
+
+    const int b = blockIdx.y;
+    const int D = P.D, N = P.N, k = P.k, stride = P.plane_stride;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *feat = P.feat + (size_t)b * P.img_stride;
+    const int tile0 = blockIdx.x * TILE;
+    float *s_cn = s_m + D * K;
+
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(P.prep + (size_t)b * (D * K + K));
+        float4 *dst = reinterpret_cast<float4 *>(s_m);
+        for (int i = threadIdx.x; i < (D * K + K) / 4; i += KM_THREADS) dst[i] = src[i];
+    }
+    if (threadIdx.x < K) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        s_nchg = 0;
+        if constexpr (VEC == 4) {
+            for (int s = 0; s < KM_STAGES; ++s) {
+                mbar_init(smem_u32(&s_full[s]), 1);
+                mbar_init(smem_u32(&s_empty[s]), KM_WARPS);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
     }
     __syncthreads();
 
-    // ---- phase A: scores and labels, one pixel per thread ----
-    int my_cnt = 0;  // lane j of every warp counts cluster j (and j + 32k for K > 32: not used, K <= 32)
-    for (int t = 0; t < KM_TILES; ++t) {
-        const int p = p_base + t * KM_THREADS + threadIdx.x;
-        const bool valid = p < N;
-        const int pc = valid ? p : N - 1;
-        float s[K];
+    // ---- phase A: scores and labels for VEC consecutive pixels per thread ----
+    const int p0 = tile0 + threadIdx.x * VEC;
+    // planes are padded (VEC == 4) so a clamped vector load never leaves the plane
+    const int pl = VEC == 4 ? min(p0, stride - VEC) : min(p0, N - 1);
+    unsigned long long s2[VEC][K / 2];
 #pragma unroll
-        for (int j = 0; j < K; ++j) s[j] = s_cn[j];
-        const float *xp = feat + pc;
-#pragma unroll 4
-        for (int d = 0; d < D; ++d) {
-            const float x = __ldg(xp + (size_t)d * N);
-            const float4 *mrow = reinterpret_cast<const float4 *>(s_m + d * K);
+    for (int i = 0; i < K / 2; ++i) {
+        unsigned long long c2;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(c2) : "f"(s_cn[2 * i]), "f"(s_cn[2 * i + 1]));
 #pragma unroll
-            for (int j4 = 0; j4 < K / 4; ++j4) {
-                const float4 m = mrow[j4];
-                s[4 * j4 + 0] = fmaf(x, m.x, s[4 * j4 + 0]);
-                s[4 * j4 + 1] = fmaf(x, m.y, s[4 * j4 + 1]);
-                s[4 * j4 + 2] = fmaf(x, m.z, s[4 * j4 + 2]);
-                s[4 * j4 + 3] = fmaf(x, m.w, s[4 * j4 + 3]);
-            }
-        }
-        int best = 0;
-        float bs = s[0];
-#pragma unroll
-        for (int j = 1; j < K; ++j)
-            if (s[j] < bs) { bs = s[j]; best = j; }
-        s_lab[t * KM_THREADS + threadIdx.x] = valid ? (unsigned char)best : (unsigned char)255;
-        if (valid && P.labels) P.labels[(size_t)b * N + p] = best;
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const unsigned m = __ballot_sync(0xffffffffu, valid && best == j);
-            if (lane == j) my_cnt += __popc(m);
-        }
+        for (int v = 0; v < VEC; ++v) s2[v][i] = c2;
     }
-    if (lane < K && my_cnt) atomicAdd(&s_cnt[lane], my_cnt);
-
-    // ---- phase B: exact fixed-point centroid sums, 32 features at a time ----
-    const int n_tiles = min(KM_TILES, (N - p_base + KM_THREADS - 1) / KM_THREADS);
-    long long *my_acc = s_acc + (size_t)warp * K * 32 + lane;
-    for (int d0 = 0; d0 < D; d0 += 32) {
-        const int nd = min(32, D - d0);
-        for (int j = 0; j < K; ++j) my_acc[j * 32] = 0;
-        for (int t = 0; t < n_tiles; ++t) {
-            __syncthreads();  // slab free
-            const int p = p_base + t * KM_THREADS + threadIdx.x;
-            const int pc = p < N ? p : N - 1;
-            const float *xp = feat + (size_t)d0 * N + pc;
-#pragma unroll 8
+    if constexpr (VEC == 4) {
+        // Feature planes arrive through a KM_STAGES-deep shared-memory ring filled by the TMA
+        // engine (cp.async.bulk, one 4 KB row per plane, completion on an mbarrier): loads of the
+        // next stages are in flight while this one is consumed, at no register cost.
+        const int n_it = (D + KM_DS - 1) / KM_DS;
+        const uint32_t row_bytes = (uint32_t)min(TILE, stride - tile0) * 4u;   // multiple of 16: planes are padded
+        const float *src0 = feat + tile0;
+        auto issue = [&](int it) {   // one elected thread
+            const int s = it % KM_STAGES;
+            const int nd = min(KM_DS, D - it * KM_DS);
+            const uint32_t bar = smem_u32(&s_full[s]);
+            mbar_expect_tx(bar, row_bytes * nd);
             for (int dd = 0; dd < nd; ++dd)
-                s_q[dd * KM_QSTR + threadIdx.x] = __float2int_rn(__ldg(xp + (size_t)dd * N) * P.fix_scale);
-            __syncthreads();
-            if (lane < nd) {
-                const unsigned char *lab = s_lab + t * KM_THREADS + warp * 32;
-                const int *q = s_q + lane * KM_QSTR + warp * 32;
-#pragma unroll 4
-                for (int pp = 0; pp < 32; ++pp) {
-                    const int l = lab[pp];
-                    if (l != 255) my_acc[l * 32] += (long long)q[pp];
+                bulk_g2s(smem_u32(s_ring + ((size_t)s * KM_DS + dd) * TILE), src0 + (size_t)(it * KM_DS + dd) * stride,
+                         row_bytes, bar);
+        };
+        if (threadIdx.x == 0)
+            for (int it = 0; it < KM_STAGES - 1 && it < n_it; ++it) issue(it);
+        for (int it = 0; it < n_it; ++it) {
+            const int s = it % KM_STAGES;
+            // refill the stage that was consumed in the previous iteration
+            if (threadIdx.x == 0 && it + KM_STAGES - 1 < n_it) {
+                const int nxt = it + KM_STAGES - 1;
+                if (nxt >= KM_STAGES) mbar_wait(smem_u32(&s_empty[nxt % KM_STAGES]), ((nxt / KM_STAGES) - 1) & 1);
+                issue(nxt);
+            }
+            mbar_wait(smem_u32(&s_full[s]), (it / KM_STAGES) & 1);
+            const float4 *xrow = reinterpret_cast<const float4 *>(s_ring + (size_t)s * KM_DS * TILE) + threadIdx.x;
+#pragma unroll
+            for (int dd = 0; dd < KM_DS; ++dd) {
+                const int d = it * KM_DS + dd;
+                if (d < D) {
+                    const float4 t = xrow[dd * (TILE / 4)];
+                    const float x[4] = {t.x, t.y, t.z, t.w};
+                    const ulonglong2 *mrow = reinterpret_cast<const ulonglong2 *>(s_m + d * K);
+#pragma unroll
+                    for (int q = 0; q < K / 4; ++q) {
+                        const ulonglong2 mm = mrow[q];
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            ffma2(s2[v][2 * q], mm.x, x[v % 4]);
+                            ffma2(s2[v][2 * q + 1], mm.y, x[v % 4]);
+                        }
+                    }
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_empty[s]));
         }
-        __syncthreads();
-        // reduce the warp-private bins and publish: one global atomic per (cluster, feature) per CTA
-        for (int i = threadIdx.x; i < K * 32; i += KM_THREADS) {
-            const int j = i >> 5, dl = i & 31;
-            if (j < k && dl < nd) {
-                long long v = 0;
+        __syncthreads();   // the ring is reused by phase B
+    } else {
+        const float *xp = feat + pl;
+#pragma unroll 4
+        for (int d = 0; d < D; ++d) {
+            const float x = __ldg(xp + (size_t)d * stride);
+            const ulonglong2 *mrow = reinterpret_cast<const ulonglong2 *>(s_m + d * K);
 #pragma unroll
-                for (int w = 0; w < KM_WARPS; ++w) v += s_acc[(size_t)w * K * 32 + i];
-                if (v) atomicAdd(reinterpret_cast<unsigned long long *>(P.sums + ((size_t)b * k + j) * D + d0 + dl),
-                                 (unsigned long long)v);
+            for (int q = 0; q < K / 4; ++q) {
+                const ulonglong2 mm = mrow[q];
+                ffma2(s2[0][2 * q], mm.x, x);
+                ffma2(s2[0][2 * q + 1], mm.y, x);
+            }
+        }
+    }
+    {
+        int newl[VEC], oldl[VEC];
+        bool chg[VEC];
+        unsigned prev = 0xffffffffu;
+        unsigned char *lab = P.lab8 + (size_t)b * P.lab_stride;
+        if (!P.first) {
+            if (VEC == 4) prev = *reinterpret_cast<const unsigned *>(lab + min(p0, P.lab_stride - 4));
+            else prev = lab[min(p0, N - 1)];
+        }
+        unsigned packed = 0;
+        int nchg = 0;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            float bs, sj[2];
+            int best = 0;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(sj[0]), "=f"(sj[1]) : "l"(s2[v][0]));
+            bs = sj[0];
+            if (sj[1] < bs) { bs = sj[1]; best = 1; }
+#pragma unroll
+            for (int i = 1; i < K / 2; ++i) {
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(sj[0]), "=f"(sj[1]) : "l"(s2[v][i]));
+                if (sj[0] < bs) { bs = sj[0]; best = 2 * i; }
+                if (sj[1] < bs) { bs = sj[1]; best = 2 * i + 1; }
+            }
+            const bool valid = p0 + v < N;
+            newl[v] = best;
+            oldl[v] = P.first ? KM_NONE : (int)((prev >> (8 * v)) & 0xffu);
+            chg[v] = valid && best != oldl[v];
+            nchg += chg[v];
+            packed |= (unsigned)best << (8 * v);
+            if (valid && P.labels_out) P.labels_out[(size_t)b * N + p0 + v] = best;
+        }
+        if (VEC == 4) {
+            if (p0 + 3 < P.lab_stride) *reinterpret_cast<unsigned *>(lab + p0) = packed;
+        } else if (p0 < N) {
+            lab[p0] = (unsigned char)packed;
+        }
+        // everything below only concerns changed pixels: skip whole warps without any
+        if (__any_sync(0xffffffffu, nchg != 0)) {
+            // cluster population deltas: lane j of every warp owns cluster j
+            int dcnt = 0;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const unsigned in = __ballot_sync(0xffffffffu, chg[v] && newl[v] == j);
+                    const unsigned out = __ballot_sync(0xffffffffu, chg[v] && oldl[v] == j);
+                    if (lane == j) dcnt += __popc(in) - __popc(out);
+                }
+            if (lane < K && dcnt) atomicAdd(&s_cnt[lane], dcnt);
+            // compact the changed pixels in pixel order
+            int incl = nchg;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int base = 0;
+            if (lane == 31) base = atomicAdd(&s_nchg, incl);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            int pos = base + incl - nchg;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                if (chg[v]) {
+                    s_ent[pos] = (unsigned short)(threadIdx.x * VEC + v);
+                    s_new[pos] = (unsigned char)newl[v];
+                    s_old[pos] = (unsigned char)oldl[v];
+                    ++pos;
+                }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: exact fixed-point centroid deltas from the changed pixels ----
+#ifdef KM_SKIP_B   // timing experiment only: wrong results
+    const int n_chg = 0;
+#else
+    const int n_chg = s_nchg;
+#endif
+    if (n_chg > 0 && n_chg <= KM_SPARSE && D * KM_SSTR <= 32 * KM_QSTR) {
+        // sparse: gather every feature of the few changed pixels at once
+        {
+            const int e = lane, g = warp;                       // entry, feature group
+            const int dg = (D + KM_WARPS - 1) / KM_WARPS;
+            if (e < n_chg) {
+                const float *xp = feat + tile0 + s_ent[e];
+                const int d1 = min(D, (g + 1) * dg);
+#pragma unroll 4
+                for (int d = g * dg; d < d1; ++d)
+                    s_q[d * KM_SSTR + e] = __float2int_rn(__ldg(xp + (size_t)d * stride) * P.fix_scale);
             }
         }
         __syncthreads();
+        for (int d = warp * 32 + lane; d < D; d += KM_THREADS) {   // lane = feature: no reduction needed
+            long long acc[NACC];
+            long long *bins = s_acc + (size_t)warp * K * 32 + lane;
+            if constexpr (K <= 8) {
+#pragma unroll
+                for (int j = 0; j < NACC; ++j) acc[j] = 0;
+            } else {
+                for (int j = 0; j < K; ++j) bins[j * 32] = 0;
+            }
+            const int *q = s_q + d * KM_SSTR;
+            for (int e = 0; e < n_chg; ++e) km_move<K>(acc, bins, s_new[e], s_old[e], (long long)q[e]);
+            unsigned long long *dst = reinterpret_cast<unsigned long long *>(P.sums + (size_t)b * k * D + d);
+            if constexpr (K <= 8) {
+#pragma unroll
+                for (int j = 0; j < NACC; ++j)
+                    if (j < k && acc[j]) atomicAdd(dst + (size_t)j * D, (unsigned long long)acc[j]);
+            } else {
+                for (int j = 0; j < k; ++j)
+                    if (bins[j * 32]) atomicAdd(dst + (size_t)j * D, (unsigned long long)bins[j * 32]);
+            }
+        }
+    } else if (n_chg > 0) {
+        for (int d0 = 0; d0 < D; d0 += 32) {
+            const int nd = min(32, D - d0);
+            long long acc[NACC];
+            long long *bins = s_acc + (size_t)warp * K * 32 + lane;
+            if constexpr (K <= 8) {
+#pragma unroll
+                for (int j = 0; j < NACC; ++j) acc[j] = 0;
+            } else {
+                for (int j = 0; j < K; ++j) bins[j * 32] = 0;
+            }
+            for (int r0 = 0; r0 < n_chg; r0 += KM_ROUND) {
+                __syncthreads();  // slab free
+                const int cnt = min(KM_ROUND, n_chg - r0);
+                if ((int)threadIdx.x < cnt) {
+                    const float *xp = feat + (size_t)d0 * stride + tile0 + s_ent[r0 + threadIdx.x];
+#pragma unroll 8
+                    for (int dd = 0; dd < nd; ++dd)
+                        s_q[dd * KM_QSTR + threadIdx.x] = __float2int_rn(__ldg(xp + (size_t)dd * stride) * P.fix_scale);
+                }
+                __syncthreads();
+                const int e0 = warp * 32, e1 = min(e0 + 32, cnt);
+                if (lane < nd) {
+                    const int *q = s_q + lane * KM_QSTR;
+                    for (int e = e0; e < e1; ++e) km_move<K>(acc, bins, s_new[r0 + e], s_old[r0 + e], (long long)q[e]);
+                }
+            }
+            if constexpr (K <= 8) {
+#pragma unroll
+                for (int j = 0; j < NACC; ++j) bins[j * 32] = acc[j];
+            }
+            __syncthreads();
+            // reduce the warp-private bins and publish: one global atomic per (cluster, feature) per CTA
+            for (int i = threadIdx.x; i < K * 32; i += KM_THREADS) {
+                const int j = i >> 5, dl = i & 31;
+                if (j < k && dl < nd) {
+                    long long v = 0;
+#pragma unroll
+                    for (int w = 0; w < KM_WARPS; ++w) v += s_acc[(size_t)w * K * 32 + i];
+                    if (v) atomicAdd(reinterpret_cast<unsigned long long *>(P.sums + ((size_t)b * k + j) * D + d0 + dl),
+                                     (unsigned long long)v);
+                }
+            }
+            __syncthreads();  // bins are re-zeroed by the next slab
+        }
     }
     if (threadIdx.x < k && s_cnt[threadIdx.x]) atomicAdd(P.counts + b * k + threadIdx.x, s_cnt[threadIdx.x]);
 
-    // ---- last CTA of this image: sums -> next centroids, and reset the accumulators ----
+    // ---- last CTA of this image: sums -> next centroids and next score table ----
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(P.done + b, 1) == P.chunks - 1);
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    float *cout = P.cent_out + (size_t)b * k * D;
-    long long *sums = P.sums + (size_t)b * k * D;
+    float *cent = P.cent + (size_t)b * k * D;
+    const long long *sums = P.sums + (size_t)b * k * D;
     for (int i = threadIdx.x; i < k * D; i += KM_THREADS) {
         const int j = i / D;
         const int cnt = __ldcg(P.counts + b * k + j);
-        float c = cin[i];
         if (cnt > 0) {
             const double den = __dmul_rn((double)cnt, (double)P.fix_scale);
-            c = __double2float_rn(__ddiv_rn((double)__ldcg(sums + i), den));
+            cent[i] = __double2float_rn(__ddiv_rn((double)__ldcg(sums + i), den));
         }
-        cout[i] = c;
-        sums[i] = 0;
     }
-    __syncthreads();
-    if (threadIdx.x < k) P.counts[b * k + threadIdx.x] = 0;
     if (threadIdx.x == 0) P.done[b] = 0;
+    __syncthreads();
+    km_write_prep(cent, P.prep + (size_t)b * (D * K + K), D, k, K);
 }
 
-template <int K>
+template <int K, int VEC>
 int launch_pass(const KmParams &P, int B, cudaStream_t st)
 {
-    const size_t smem = sizeof(float) * (size_t)((P.D * K + 3) & ~3) + sizeof(long long) * (size_t)KM_WARPS * K * 32 +
-                        sizeof(int) * (size_t)32 * KM_QSTR;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GCIS_CUDA_TRY(cudaFuncSetAttribute(km_pass_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    const size_t smem = km_smem_bytes(K, VEC, P.D);
     if (smem > 200 * 1024) return set_error(GCIS_E_INVALID, "kmeans: D=%d too large for shared memory", P.D);
-    km_pass_kernel<K><<<dim3(P.chunks, B), KM_THREADS, smem, st>>>(P);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        GCIS_CUDA_TRY(cudaFuncSetAttribute(km_pass_kernel<K, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    km_pass_kernel<K, VEC><<<dim3(P.chunks, B), KM_THREADS, smem, st>>>(P);
     GCIS_LAUNCH_CHECK();
     return GCIS_OK;
 }
 
-}  // namespace
-
-size_t kmeans_workspace_bytes(int B, int D, int k)
+template <int VEC>
+int launch_pass_k(const KmParams &P, int B, cudaStream_t st)
 {
-    return sizeof(float) * (size_t)2 * B * k * D + sizeof(long long) * (size_t)B * k * D + sizeof(int) * (size_t)B * (k + 1) + 64;
+    if (P.k <= 8) return launch_pass<8, VEC>(P, B, st);
+    if (P.k <= 16) return launch_pass<16, VEC>(P, B, st);
+    return launch_pass<32, VEC>(P, B, st);
 }
 
-// d_ws: workspace of kmeans_workspace_bytes(B, D, k), 16-byte aligned.
-int kmeans_launch(const float *d_feat, int B, int D, int N, int k, int iters, int fix_shift,
-                  const int32_t *d_init_idx, int32_t *d_labels, float *d_centroids, void *d_ws, cudaStream_t st)
+}  // namespace
+
+static size_t km_lab_stride(int N) { return (size_t)round_up(N, 16); }
+static int km_pad_k(int k) { return k <= 8 ? 8 : (k <= 16 ? 16 : 32); }
+
+size_t kmeans_workspace_bytes(int B, int D, int N, int k)
+{
+    const int K = km_pad_k(k);
+    return sizeof(float) * (size_t)B * k * D + sizeof(float) * (size_t)B * (D * K + K) +
+           sizeof(long long) * (size_t)B * k * D + sizeof(int) * (size_t)B * (k + 1) + (size_t)B * km_lab_stride(N) + 512;
+}
+
+// d_feat: [B] images of D planes, `plane_stride` floats apart, images `img_stride` floats apart.
+// d_ws: workspace of kmeans_workspace_bytes(B, D, N, k), 16-byte aligned.
+int kmeans_launch(const float *d_feat, size_t img_stride, int plane_stride, int B, int D, int N, int k, int iters,
+                  int fix_shift, const int32_t *d_init_idx, int32_t *d_labels, float *d_centroids, void *d_ws,
+                  cudaStream_t st)
 {
     if (k < 1 || k > 32) return set_error(GCIS_E_INVALID, "kmeans: k=%d outside 1..32", k);
     if (iters < 1) return set_error(GCIS_E_INVALID, "kmeans: iters=%d < 1", iters);
     if (fix_shift < 0 || fix_shift > 30) return set_error(GCIS_E_INVALID, "kmeans: fix_shift=%d outside 0..30", fix_shift);
     if (B > 65535) return set_error(GCIS_E_INVALID, "kmeans: B=%d > 65535 per call", B);
+    const int K = km_pad_k(k);
+    auto align16 = [](char *p) { return reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15); };
     char *w = static_cast<char *>(d_ws);
-    long long *sums = reinterpret_cast<long long *>(w);
-    w += sizeof(long long) * (size_t)B * k * D;
-    float *cent[2];
-    cent[0] = reinterpret_cast<float *>(w); w += sizeof(float) * (size_t)B * k * D;
-    cent[1] = reinterpret_cast<float *>(w); w += sizeof(float) * (size_t)B * k * D;
+    long long *sums = reinterpret_cast<long long *>(w); w += sizeof(long long) * (size_t)B * k * D;
+    w = align16(w);
+    float *prep = reinterpret_cast<float *>(w); w += sizeof(float) * (size_t)B * (D * K + K);
+    float *cent = reinterpret_cast<float *>(w); w += sizeof(float) * (size_t)B * k * D;
     int *counts = reinterpret_cast<int *>(w); w += sizeof(int) * (size_t)B * k;
-    int *done = reinterpret_cast<int *>(w);
+    int *done = reinterpret_cast<int *>(w); w += sizeof(int) * (size_t)B;
+    unsigned char *lab8 = reinterpret_cast<unsigned char *>(align16(w));
 
-    km_init_kernel<<<B, 256, 0, st>>>(d_feat, d_init_idx, cent[0], sums, counts, done, D, N, k);
+    km_init_kernel<<<B, 256, 0, st>>>(d_feat, img_stride, plane_stride, d_init_idx, cent, prep, sums, counts, done, D, N, k, K);
     GCIS_LAUNCH_CHECK();
+    // 128-bit loads need 16-byte aligned, padded planes; otherwise one pixel per thread
+    const bool vec4 = plane_stride % 4 == 0 && plane_stride >= round_up(N, 4) && img_stride % 4 == 0 &&
+                      (reinterpret_cast<uintptr_t>(d_feat) & 15) == 0;
     KmParams P;
-    P.feat = d_feat; P.sums = sums; P.counts = counts; P.done = done;
-    P.D = D; P.N = N; P.k = k; P.chunks = ceil_div(N, KM_PX);
+    P.feat = d_feat; P.img_stride = img_stride; P.plane_stride = plane_stride;
+    P.cent = cent; P.prep = prep; P.sums = sums; P.counts = counts; P.done = done;
+    P.lab8 = lab8; P.lab_stride = (int)km_lab_stride(N);
+    P.D = D; P.N = N; P.k = k; P.chunks = ceil_div(N, KM_THREADS * (vec4 ? 4 : 1));
     P.fix_scale = (float)(1u << fix_shift);
     for (int t = 0; t < iters; ++t) {
-        P.cent_in = cent[t & 1];
-        P.cent_out = cent[(t + 1) & 1];
-        P.labels = (t == iters - 1) ? d_labels : nullptr;
-        int rc;
-        if (k <= 8) rc = launch_pass<8>(P, B, st);
-        else if (k <= 16) rc = launch_pass<16>(P, B, st);
-        else rc = launch_pass<32>(P, B, st);
+        P.labels_out = (t == iters - 1) ? d_labels : nullptr;
+        P.first = t == 0;
+        const int rc = vec4 ? launch_pass_k<4>(P, B, st) : launch_pass_k<1>(P, B, st);
         if (rc) return rc;
     }
     if (d_centroids)
-        GCIS_CUDA_TRY(cudaMemcpyAsync(d_centroids, cent[iters & 1], sizeof(float) * (size_t)B * k * D,
-                                      cudaMemcpyDeviceToDevice, st));
+        GCIS_CUDA_TRY(cudaMemcpyAsync(d_centroids, cent, sizeof(float) * (size_t)B * k * D, cudaMemcpyDeviceToDevice, st));
     return GCIS_OK;
 }
 

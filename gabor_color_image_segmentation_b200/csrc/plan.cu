@@ -36,12 +36,12 @@ int label_metrics_launch(const int32_t *, const uint16_t *, const int32_t *, int
                          int64_t *, int64_t *, int32_t *, int32_t *, int32_t *, int32_t *, int32_t *, int32_t *,
                          cudaStream_t);
 int find_boundaries_launch(const int32_t *, uint8_t *, int, int, int, cudaStream_t);
-size_t kmeans_workspace_bytes(int B, int D, int k);
-int kmeans_launch(const float *, int, int, int, int, int, int, const int32_t *, int32_t *, float *, void *,
-                  cudaStream_t);
+size_t kmeans_workspace_bytes(int B, int D, int N, int k);
+int kmeans_launch(const float *, size_t, int, int, int, int, int, int, int, const int32_t *, int32_t *, float *,
+                  void *, cudaStream_t);
 GaborLaunchPlan *gabor_plan_new(const GaborBankHost &, int H, int W, int C, int P, int Wp, int feature, size_t *smem);
 void gabor_plan_delete(GaborLaunchPlan *);
-int gabor_launch(GaborLaunchPlan &, const float *, float *, const float *, const GaborScale *, int, cudaStream_t);
+int gabor_launch(GaborLaunchPlan &, const float *, float *, const float *, const GaborScale *, int, int, cudaStream_t);
 
 }  // namespace gcis
 
@@ -52,7 +52,7 @@ struct gcis_plan {
     std::vector<double> freqs, thetas;
     GaborBankHost bank;
     GaborLaunchPlan *glp = nullptr;
-    int D = 0, N = 0, P = 0, Wp = 0, group = 1;
+    int D = 0, N = 0, Np = 0, P = 0, Wp = 0, group = 1;
     size_t bytes = 0;
     // device workspaces
     float *d_taps = nullptr;
@@ -120,15 +120,19 @@ int segment_group(gcis_plan *p, const uint8_t *d_img, int nb, const int32_t *d_i
                   float *d_feat_out, cudaStream_t st, int group_index)
 {
     const gcis_config &c = p->cfg;
+    // the plan's own feature buffer pads every plane to Np floats so the k-means pass can use
+    // aligned 128-bit loads; a caller-supplied tensor is dense [D][H][W]
     float *feat = d_feat_out ? d_feat_out : p->d_feat;
+    const int pstride = d_feat_out ? p->N : p->Np;
     const bool prof = p->profiling && group_index >= 0;
     if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 0), st);
     TRY(colour_planes_launch(d_img, p->d_planes, nb, c.height, c.width, p->P, p->Wp, c.colour_space, st));
     if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 1), st);
-    TRY(gabor_launch(*p->glp, p->d_planes, feat, p->d_taps, p->d_scales, nb, st));
+    TRY(gabor_launch(*p->glp, p->d_planes, feat, p->d_taps, p->d_scales, nb, pstride, st));
     if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 2), st);
     if (d_labels) {
-        TRY(kmeans_launch(feat, nb, p->D, p->N, c.k, c.iters, c.fix_shift, d_init, d_labels, nullptr, p->d_km_ws, st));
+        TRY(kmeans_launch(feat, (size_t)p->D * pstride, pstride, nb, p->D, p->N, c.k, c.iters, c.fix_shift, d_init,
+                          d_labels, nullptr, p->d_km_ws, st));
         if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 3), st);
     }
     return GCIS_OK;
@@ -203,6 +207,7 @@ int32_t gcis_plan_create(const gcis_config *cfg, gcis_plan **out)
     p->D = 3 * cfg->n_scales * cfg->n_orient;
     p->P = p->bank.hmax;
     p->Wp = round_up(W + 2 * p->P + 8, 4);
+    p->Np = round_up(p->N, 32);
     int group = cfg->group;
     if (const char *e = getenv("GCIS_GROUP")) group = atoi(e);
     if (group <= 0) group = 2;
@@ -221,10 +226,10 @@ int32_t gcis_plan_create(const gcis_config *cfg, gcis_plan **out)
     PA(p->d_taps, p->bank.taps.size());
     PA(p->d_scales, p->bank.scales.size());
     PA(p->d_planes, (size_t)p->group * 3 * H * p->Wp);
-    PA(p->d_feat, (size_t)p->group * p->D * p->N);
+    PA(p->d_feat, (size_t)p->group * p->D * p->Np);
     {
         char *ws = nullptr;
-        int rc2 = dev_alloc(&ws, kmeans_workspace_bytes(p->group, p->D, cfg->k), &p->bytes);
+        int rc2 = dev_alloc(&ws, kmeans_workspace_bytes(p->group, p->D, p->N, cfg->k), &p->bytes);
         if (rc2) return fail(rc2);
         p->d_km_ws = ws;
     }
@@ -302,7 +307,7 @@ int32_t gcis_kmeans(gcis_plan *p, const float *d_feat, int32_t B, const int32_t 
     const size_t feat_stride = (size_t)p->D * p->N;
     for (int b0 = 0; b0 < B; b0 += p->group) {
         const int nb = std::min(p->group, B - b0);
-        TRY(kmeans_launch(d_feat + b0 * feat_stride, nb, p->D, p->N, c.k, c.iters, c.fix_shift, d_init_idx + (size_t)b0 * c.k,
+        TRY(kmeans_launch(d_feat + b0 * feat_stride, feat_stride, p->N, nb, p->D, p->N, c.k, c.iters, c.fix_shift, d_init_idx + (size_t)b0 * c.k,
                           d_labels + (size_t)b0 * p->N, d_centroids ? d_centroids + (size_t)b0 * c.k * p->D : nullptr,
                           p->d_km_ws, st));
     }

@@ -138,12 +138,16 @@ def test_kmeans_ties_and_empty_clusters():
     f = np.zeros((1, 3, N), np.float32)
     f[0, 0, :200] = 0.0; f[0, 0, 200:400] = 1.0; f[0, 0, 400:] = 0.5    # third block equidistant
     idx = np.array([[0, 200, 1]], np.int32)                             # cluster 2 duplicates cluster 0
-    labels, cent = _kmeans_raw(f, idx, 3, 3)
-    ol, oc, _ = orc.kmeans(f[0], 3, 3, idx[0])
-    np.testing.assert_array_equal(labels[0], ol)
-    np.testing.assert_array_equal(cent[0], oc)
-    assert (labels[0] != 2).all()          # duplicate never wins a tie (lowest index) and keeps its centroid
-    assert cent[0, 2, 0] == 0.0
+    for T in (1, 3):
+        labels, cent = _kmeans_raw(f, idx, 3, T)
+        ol, oc, _ = orc.kmeans(f[0], 3, T, idx[0])
+        np.testing.assert_array_equal(labels[0], ol)
+        np.testing.assert_array_equal(cent[0], oc)
+        if T == 1:
+            # ties go to the lowest index: the duplicate (cluster 2) wins nothing, the equidistant
+            # block joins cluster 0, and the empty cluster keeps its centroid
+            assert (labels[0, :200] == 0).all() and (labels[0, 200:400] == 1).all() and (labels[0, 400:] == 0).all()
+            assert cent[0, 2, 0] == 0.0 and cent[0, 1, 0] == 1.0 and cent[0, 0, 0] == 0.25
 
 
 def test_segment_pipeline_against_oracle():

@@ -198,117 +198,174 @@ struct GaborParams {
     int order[GB_MAX_SCALES];    // scale handled by range i
     int nsrc_cap;                // rows of T the shared buffer holds
     int istr;                    // chunk row stride (odd)
-    int tap_slot;                // floats reserved per tap array in shared memory
+    int tap_slot;                // floats reserved per staged filter (complex, interleaved) in shared memory
     int rowtab_cap;
 };
 
-// out[i] += sum_u g[i + 2h - u] * x[u],  i < R, u < nsteps: the register-blocked sliding window
-// both passes share.  g is stored zero-padded (GB_TAP_PAD each side); every R steps the window
-// of 2R-1 taps slides by R with aligned 128-bit shared loads.
-template <int R, bool XI, bool GI, class XLoad>
-__device__ __forceinline__ void sweep(XLoad xload, const float *gr, const float *gi, int h, float (&A)[R],
-                                      float (&Bv)[R], float (&Cv)[R], float (&Dv)[R])
+typedef unsigned long long u64;
+
+// acc.{lo,hi} += a.{lo,hi} * s: one packed FP32 FMA (fma.rn.f32x2, sm_100+), half the issue slots
+__device__ __forceinline__ void fma2_vs(u64 &acc, u64 a, float s)
 {
-    float wr[2 * R - 1], wi[2 * R - 1];
-    int idx = GB_TAP_PAD + 2 * h - R + 1;
-#pragma unroll
-    for (int t = 0; t < 2 * R - 1; ++t) {
-        wr[t] = gr[idx + t];
-        wi[t] = GI ? gi[idx + t] : 0.f;
-    }
-    const int nsteps = (2 * h + R + R - 1) / R * R;
+    u64 b;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(s));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+// Register-blocked sliding window shared by both passes:
+//     out[i] += sum_u g[i + 2h - u] * x[u],   i < R, u < nblk*R
+// The 2R-1 taps a block of R inputs needs are re-read each block with aligned 128-bit shared
+// loads (broadcast, one wavefront each).  Complex taps are stored interleaved (re, im), so one
+// packed FMA updates the (re*x, im*x) pair of an output; with real taps and complex inputs the
+// pair is (w*xr, w*xi).
+//   CT: complex taps     CX: complex input
+//   CT &&  CX: P[i] = (A, D) += W*xr,  Q[i] = (C, B) += W*xi
+//   CT && !CX: P[i] = (A, D) += W*x
+//  !CT &&  CX: P[i] = (A, C) += w*X
+//  !CT && !CX: S[i] = A      += w*x
+// w0 points at the window of block 0; the window moves down by R taps per block.
+template <int R, bool CT, bool CX, class XLoad>
+__device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u64 (&P)[R], u64 (&Q)[R], float (&S)[R])
+{
 #pragma unroll 1
-    for (int ub = 0; ub < nsteps; ub += R) {
-        if (ub) {
+    for (int m = 0; m < nblk; ++m) {
+        u64 wc[CT ? 2 * R : 1];
+        float wr[CT ? 1 : 2 * R];
+        if constexpr (CT) {
+            const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(w0 - (size_t)m * 2 * R);
 #pragma unroll
-            for (int t = 2 * R - 2; t >= R; --t) {
-                wr[t] = wr[t - R];
-                if (GI) wi[t] = wi[t - R];
+            for (int q = 0; q < R; ++q) {
+                const ulonglong2 v = wp[q];
+                wc[2 * q] = v.x; wc[2 * q + 1] = v.y;
             }
-            idx -= R;
+        } else {
+            const float4 *wp = reinterpret_cast<const float4 *>(w0 - (size_t)m * R);
 #pragma unroll
-            for (int t = 0; t < R; t += 4) {
-                const float4 v = *reinterpret_cast<const float4 *>(gr + idx + t);
-                wr[t] = v.x; wr[t + 1] = v.y; wr[t + 2] = v.z; wr[t + 3] = v.w;
-                if (GI) {
-                    const float4 q = *reinterpret_cast<const float4 *>(gi + idx + t);
-                    wi[t] = q.x; wi[t + 1] = q.y; wi[t + 2] = q.z; wi[t + 3] = q.w;
-                }
+            for (int q = 0; q < R / 2; ++q) {
+                const float4 v = wp[q];
+                wr[4 * q] = v.x; wr[4 * q + 1] = v.y; wr[4 * q + 2] = v.z; wr[4 * q + 3] = v.w;
             }
         }
+        float xr[R], xi[R];
+        u64 xp[R];
+#pragma unroll
+        for (int uu = 0; uu < R; ++uu) xload(m * R + uu, xr[uu], xi[uu], xp[uu]);
 #pragma unroll
         for (int uu = 0; uu < R; ++uu) {
-            float xr, xi;
-            xload(ub + uu, xr, xi);
 #pragma unroll
             for (int i = 0; i < R; ++i) {
                 const int t = i - uu + R - 1;
-                A[i] = fmaf(wr[t], xr, A[i]);
-                if (XI) Cv[i] = fmaf(wr[t], xi, Cv[i]);
-                if (GI) Dv[i] = fmaf(wi[t], xr, Dv[i]);
-                if (XI && GI) Bv[i] = fmaf(wi[t], xi, Bv[i]);
+                if constexpr (CT) {
+                    fma2_vs(P[i], wc[t], xr[uu]);
+                    if constexpr (CX) fma2_vs(Q[i], wc[t], xi[uu]);
+                } else if constexpr (CX) {
+                    fma2_vs(P[i], xp[uu], wr[t]);
+                } else {
+                    S[i] = fmaf(wr[t], xr[uu], S[i]);
+                }
             }
         }
     }
 }
 
-template <bool GI>
-__device__ __forceinline__ void row_pass_chunk(const float *chunk, int istr, const float *gr, const float *gi, int h,
-                                               float *Tre, float *Tim, int trow, bool active)
+// Row pass of one staged chunk: lane = image row, warp = block of GB_RR output columns.
+template <bool CT>
+__device__ __forceinline__ void row_pass_chunk(const float *chunk, int istr, const float *w0, int nblk, float2 *T,
+                                               int trow, bool active)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int xb = warp * GB_RR;
-    float A[GB_RR], Bv[GB_RR], Cv[GB_RR], Dv[GB_RR];
+    u64 Pv[GB_RR], Qv[GB_RR];
+    float Sv[GB_RR];
 #pragma unroll
-    for (int i = 0; i < GB_RR; ++i) { A[i] = 0.f; Bv[i] = 0.f; Cv[i] = 0.f; Dv[i] = 0.f; }
+    for (int i = 0; i < GB_RR; ++i) { Pv[i] = 0ull; Qv[i] = 0ull; Sv[i] = 0.f; }
     const float *src = chunk + lane * istr + xb;
-    sweep<GB_RR, false, GI>([&](int u, float &xr, float &xi) { xr = src[u]; xi = 0.f; }, gr, gi, h, A, Bv, Cv, Dv);
+    sweep<GB_RR, CT, false>([&](int u, float &xr, float &xi, u64 &xp) { xr = src[u]; xi = 0.f; xp = 0ull; }, w0, nblk, Pv,
+                            Qv, Sv);
     if (active) {
+        u64 *dst = reinterpret_cast<u64 *>(T + (size_t)trow * GB_TWP + xb);
 #pragma unroll
         for (int i = 0; i < GB_RR; ++i) {
-            Tre[trow * GB_TWP + xb + i] = A[i];
-            if (GI) Tim[trow * GB_TWP + xb + i] = Dv[i];
+            if constexpr (CT) dst[i] = Pv[i];                      // (Tr, Ti)
+            else T[(size_t)trow * GB_TWP + xb + i] = make_float2(Sv[i], 0.f);
         }
     }
 }
 
-template <bool XI, bool GI>
-__device__ __forceinline__ void col_pass(const GaborParams &P, const float *Tre, const float *Tim, const int *rowtab,
-                                         const float *gr, const float *gi, int h, int y0, int th, int x0,
-                                         float *feat0, float *feat1)
+// Column pass: lane = column of the strip, warp = blocks of GB_RC output rows.
+template <bool CX, bool CT>
+__device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, const int *rowtab, const float *w0,
+                                         int nblk, int y0, int th, int x0, float *feat0, float *feat1)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nrb = (th + GB_RC - 1) / GB_RC;
     const bool col_ok = x0 + lane < P.W;
+    const u64 *Tl = reinterpret_cast<const u64 *>(T) + lane;
     for (int rb = warp; rb < nrb; rb += GB_WARPS) {
-        float A[GB_RC], Bv[GB_RC], Cv[GB_RC], Dv[GB_RC];
+        u64 Pv[GB_RC], Qv[GB_RC];
+        float Sv[GB_RC];
 #pragma unroll
-        for (int i = 0; i < GB_RC; ++i) { A[i] = 0.f; Bv[i] = 0.f; Cv[i] = 0.f; Dv[i] = 0.f; }
+        for (int i = 0; i < GB_RC; ++i) { Pv[i] = 0ull; Qv[i] = 0ull; Sv[i] = 0.f; }
         const int *rt = rowtab + rb * GB_RC;
-        sweep<GB_RC, XI, GI>(
-            [&](int u, float &xr, float &xi) {
-                const int o = rt[u] + lane;
-                xr = Tre[o];
-                xi = XI ? Tim[o] : 0.f;
+        sweep<GB_RC, CT, CX>(
+            [&](int u, float &xr, float &xi, u64 &xp) {
+                xp = Tl[rt[u]];
+                unpack2(xp, xr, xi);
             },
-            gr, gi, h, A, Bv, Cv, Dv);
+            w0, nblk, Pv, Qv, Sv);
 #pragma unroll
         for (int i = 0; i < GB_RC; ++i) {
             const int r = rb * GB_RC + i;
             if (r < th && col_ok) {
+                float A, Bv = 0.f, Cv = 0.f, Dv = 0.f;
+                if constexpr (CT) {
+                    unpack2(Pv[i], A, Dv);
+                    if constexpr (CX) unpack2(Qv[i], Cv, Bv);
+                } else if constexpr (CX) {
+                    unpack2(Pv[i], A, Cv);
+                } else {
+                    A = Sv[i];
+                }
                 // theta: (A - B) + i(C + D);  pi - theta: (A + B) + i(D - C)
-                const float re0 = A[i] - Bv[i], im0 = Cv[i] + Dv[i];
-                float e0 = fmaf(re0, re0, im0 * im0);
+                const float re0 = A - Bv, im0 = Cv + Dv;
+                const float e0 = fmaf(re0, re0, im0 * im0);
                 const size_t o = (size_t)(y0 + r) * P.W + x0 + lane;
                 feat0[o] = P.feature == GCIS_FEATURE_MAGNITUDE ? sqrtf(e0) : e0;
                 if (feat1) {
-                    const float re1 = A[i] + Bv[i], im1 = Dv[i] - Cv[i];
-                    float e1 = fmaf(re1, re1, im1 * im1);
+                    const float re1 = A + Bv, im1 = Dv - Cv;
+                    const float e1 = fmaf(re1, re1, im1 * im1);
                     feat1[o] = P.feature == GCIS_FEATURE_MAGNITUDE ? sqrtf(e1) : e1;
                 }
             }
         }
     }
+}
+
+// Copy one filter's taps from the global table into shared memory in the layout sweep() reads:
+// complex -> interleaved (re, im) with tap j at complex index 1 + PAD + j (window starts land on
+// 16-byte boundaries); real -> tap j at float index sr + PAD + j.  Returns the block-0 window.
+template <int R>
+__device__ __forceinline__ const float *stage_taps(float *dst, const float *taps, int off_re, int off_im, int h)
+{
+    const int ntap = 2 * h + 1 + 2 * GB_TAP_PAD;
+    if (off_im >= 0) {
+        for (int i = threadIdx.x; i < ntap + 2; i += GB_THREADS) {
+            const bool in = i >= 1 && i <= ntap;
+            dst[2 * i] = in ? taps[off_re + i - 1] : 0.f;
+            dst[2 * i + 1] = in ? taps[off_im + i - 1] : 0.f;
+        }
+        return dst + 2 * (GB_TAP_PAD + 2 * h + 2 - R);
+    }
+    const int sr = (4 - ((2 * h + 1) & 3)) & 3;
+    for (int i = threadIdx.x; i < ntap + sr + 4; i += GB_THREADS) {
+        const int j = i - sr;
+        dst[i] = (j >= 0 && j < ntap) ? taps[off_re + j] : 0.f;
+    }
+    return dst + sr + GB_TAP_PAD + 2 * h - R + 1;
 }
 
 __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_constant__ GaborParams P)
@@ -330,11 +387,11 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
     const int y0 = vt * P.TH[s];
     const int th = min(P.TH[s], P.H - y0);
 
-    float *tapbuf = smem;  // first, so the 128-bit tap loads stay 16-byte aligned
-    int *rowtab = reinterpret_cast<int *>(tapbuf + 4 * P.tap_slot);
-    float *Tre = reinterpret_cast<float *>(rowtab + P.rowtab_cap);
-    float *Tim = Tre + (size_t)P.nsrc_cap * GB_TWP;
-    float *chunk = Tim + (size_t)P.nsrc_cap * GB_TWP;
+    float *tap_row = smem;                       // first, so the 128-bit tap loads stay 16-byte aligned
+    float *tap_col = tap_row + P.tap_slot;
+    int *rowtab = reinterpret_cast<int *>(tap_col + P.tap_slot);
+    float2 *T = reinterpret_cast<float2 *>(rowtab + P.rowtab_cap);   // [nsrc_cap][GB_TWP] complex row-pass output
+    float *chunk = reinterpret_cast<float *>(T + (size_t)P.nsrc_cap * GB_TWP);
 
     const GaborScale &sc = P.scales[s];
     const float *plane = P.planes + ((size_t)b * P.C + c) * P.H * P.Wp;
@@ -345,18 +402,11 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
     for (int ji = 0; ji < sc.n_jobs; ++ji) {
         const GaborJob job = sc.jobs[ji];
         const int h = job.h;
-        const int ntap = 2 * h + 1 + 2 * GB_TAP_PAD;
-        // tap arrays are placed so that the sweep's 128-bit window loads are aligned
-        const int shift = (4 - ((2 * h + 1) & 3)) & 3;
-        float *t_rr = tapbuf + shift, *t_ri = t_rr + P.tap_slot, *t_cr = t_ri + P.tap_slot, *t_ci = t_cr + P.tap_slot;
         __syncthreads();  // previous job's column pass is done with T, taps and rowtab
         if (threadIdx.x == 0) { s_lo = P.H; s_hi = 0; }
-        for (int i = threadIdx.x; i < ntap; i += GB_THREADS) {
-            t_rr[i] = P.taps[job.row_re + i];
-            t_ri[i] = job.row_im >= 0 ? P.taps[job.row_im + i] : 0.f;
-            t_cr[i] = P.taps[job.col_re + i];
-            t_ci[i] = job.col_im >= 0 ? P.taps[job.col_im + i] : 0.f;
-        }
+        const float *w_row = stage_taps<GB_RR>(tap_row, P.taps, job.row_re, job.row_im, h);
+        const float *w_col = stage_taps<GB_RC>(tap_col, P.taps, job.col_re, job.col_im, h);
+        const int nblk_row = (2 * h + GB_RR + GB_RR - 1) / GB_RR, nblk_col = (2 * h + GB_RC + GB_RC - 1) / GB_RC;
         __syncthreads();
         // rows of the image the column pass will touch (reflect-folded), and their span
         const int ne = (th + GB_RC - 1) / GB_RC * GB_RC + 2 * h + 2 * GB_RC;
@@ -388,8 +438,8 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
             __syncthreads();
             const int trow = ch0 - lo + lane;
             const bool active = ch0 + lane < hi;
-            if (job.row_im >= 0) row_pass_chunk<true>(chunk, P.istr, t_rr, t_ri, h, Tre, Tim, trow, active);
-            else row_pass_chunk<false>(chunk, P.istr, t_rr, t_ri, h, Tre, Tim, trow, active);
+            if (job.row_im >= 0) row_pass_chunk<true>(chunk, P.istr, w_row, nblk_row, T, trow, active);
+            else row_pass_chunk<false>(chunk, P.istr, w_row, nblk_row, T, trow, active);
         }
         __syncthreads();
 
@@ -397,11 +447,11 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
         const int d0 = (c * P.S + s) * P.O;
         float *f0 = featb + (size_t)(d0 + job.out0) * P.feat_plane_stride;
         float *f1 = job.out1 >= 0 ? featb + (size_t)(d0 + job.out1) * P.feat_plane_stride : nullptr;
-        const bool xi = job.row_im >= 0, gi = job.col_im >= 0;
-        if (xi && gi) col_pass<true, true>(P, Tre, Tim, rowtab, t_cr, t_ci, h, y0, th, x0, f0, f1);
-        else if (xi) col_pass<true, false>(P, Tre, Tim, rowtab, t_cr, t_ci, h, y0, th, x0, f0, f1);
-        else if (gi) col_pass<false, true>(P, Tre, Tim, rowtab, t_cr, t_ci, h, y0, th, x0, f0, f1);
-        else col_pass<false, false>(P, Tre, Tim, rowtab, t_cr, t_ci, h, y0, th, x0, f0, f1);
+        const bool cx = job.row_im >= 0, ct = job.col_im >= 0;
+        if (cx && ct) col_pass<true, true>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1);
+        else if (cx) col_pass<true, false>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1);
+        else if (ct) col_pass<false, true>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1);
+        else col_pass<false, false>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1);
     }
 }
 
@@ -428,9 +478,9 @@ struct GaborLaunchPlan {
 static size_t gabor_smem_bytes(int nsrc, int hmax, int th_max)
 {
     const int istr = (GB_TW + 2 * hmax + GB_RR) | 1;
-    const int tap_slot = ((2 * hmax + 1 + 2 * GB_TAP_PAD + 3 + 3) / 4) * 4;
+    const int tap_slot = round_up(2 * (2 * hmax + 1 + 2 * GB_TAP_PAD + 2) + 8, 4);
     const int rowtab = round_up((th_max + GB_RC - 1) / GB_RC * GB_RC + 2 * hmax + 2 * GB_RC, 4);
-    return sizeof(float) * ((size_t)2 * nsrc * GB_TWP + (size_t)GB_CHUNK * istr + 4 * (size_t)tap_slot) +
+    return sizeof(float) * ((size_t)2 * nsrc * GB_TWP + (size_t)GB_CHUNK * istr + 2 * (size_t)tap_slot) +
            sizeof(int) * (size_t)rowtab;
 }
 
@@ -473,7 +523,7 @@ int gabor_plan(const GaborBankHost &bank, int H, int W, int C, int P, int Wp, in
     for (int s = 0; s < bank.S; ++s) th_max = std::max(th_max, p.TH[s]);
     p.nsrc_cap = nsrc_cap;
     p.istr = (GB_TW + 2 * hmax + GB_RR) | 1;
-    p.tap_slot = ((2 * hmax + 1 + 2 * GB_TAP_PAD + 3 + 3) / 4) * 4;
+    p.tap_slot = round_up(2 * (2 * hmax + 1 + 2 * GB_TAP_PAD + 2) + 8, 4);
     p.rowtab_cap = round_up((th_max + GB_RC - 1) / GB_RC * GB_RC + 2 * hmax + 2 * GB_RC, 4);
     lp.smem = gabor_smem_bytes(nsrc_cap, hmax, th_max);
     // widest scale first so the long CTAs are not left for the tail

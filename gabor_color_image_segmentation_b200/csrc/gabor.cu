@@ -428,14 +428,36 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
         // ---- row pass: image rows [lo, hi) -> T (complex) in shared memory ----
         const int cw = GB_TW + 2 * h + GB_RR;            // staged columns per row
         const int gcol0 = x0 - h + P.P;                  // first staged column in the padded plane
+        // Staging: warp w owns chunk rows w, w+8, w+16, w+24; a lane covers columns lane + 32 j.
+        // The next chunk is fetched into registers while the current one is convolved, so the
+        // global-load latency hides behind the row pass.
+        const int warp = threadIdx.x >> 5;
+        constexpr int SROWS = GB_CHUNK / GB_WARPS;                       // 4 rows per warp
+        constexpr int SCOLS = (GB_TW + 2 * 96 + GB_RR + 31) / 32;        // lane columns for the widest supported row
+        const int ncol = (cw + 31) / 32;                                 // <= SCOLS (h <= 96 checked on the host)
+        float stage[SROWS][SCOLS];
+        auto fetch = [&](int ch0) {
+#pragma unroll
+            for (int a = 0; a < SROWS; ++a) {
+                const int r = ch0 + warp + a * GB_WARPS;
+                const float *src = plane + (size_t)min(r, P.H - 1) * P.Wp + gcol0 + lane;
+#pragma unroll
+                for (int j = 0; j < SCOLS; ++j) {
+                    const int cc = lane + 32 * j;
+                    stage[a][j] = (j < ncol && r < hi && cc < cw && gcol0 + cc < P.Wp) ? __ldg(src + 32 * j) : 0.f;
+                }
+            }
+        };
+        fetch(lo);
         for (int ch0 = lo; ch0 < hi; ch0 += GB_CHUNK) {
             __syncthreads();                             // chunk buffer free (and rowtab complete on 1st pass)
-            for (int i = threadIdx.x; i < GB_CHUNK * cw; i += GB_THREADS) {
-                const int rr = i / cw, cc = i - rr * cw;
-                const int r = ch0 + rr, gc = gcol0 + cc;
-                chunk[rr * P.istr + cc] = (r < hi && gc < P.Wp) ? plane[(size_t)r * P.Wp + gc] : 0.f;
-            }
+#pragma unroll
+            for (int a = 0; a < SROWS; ++a)
+#pragma unroll
+                for (int j = 0; j < SCOLS; ++j)
+                    if (j < ncol && lane + 32 * j < cw) chunk[(warp + a * GB_WARPS) * P.istr + lane + 32 * j] = stage[a][j];
             __syncthreads();
+            if (ch0 + GB_CHUNK < hi) fetch(ch0 + GB_CHUNK);
             const int trow = ch0 - lo + lane;
             const bool active = ch0 + lane < hi;
             if (job.row_im >= 0) row_pass_chunk<true>(chunk, P.istr, w_row, nblk_row, T, trow, active);
@@ -491,6 +513,7 @@ int gabor_plan(const GaborBankHost &bank, int H, int W, int C, int P, int Wp, in
     p.C = C; p.H = H; p.W = W; p.Wp = Wp; p.P = P; p.S = bank.S; p.O = bank.O; p.feature = feature;
     p.n_strips = ceil_div(W, GB_TW);
     const int hmax = bank.hmax;
+    if (hmax > 96) return set_error(GCIS_E_INVALID, "gabor: kernel half-width %d > 96 is not supported", hmax);
     const size_t two_per_sm = 112 * 1024, one_per_sm = 226 * 1024;
     size_t budget;
     int nsrc_cap;

@@ -69,14 +69,14 @@ struct KmParams {
 };
 
 // Score table of one image from its centroids (all threads of the CTA; cent must be visible).
-__device__ __forceinline__ void km_write_prep(const float *cent, float *prep, int D, int k, int K)
+__device__ __forceinline__ void km_write_prep(const float *cent, float *prep, int D, int k, int K, int tid, int nthr)
 {
-    for (int i = threadIdx.x; i < D * K; i += blockDim.x) {
+    for (int i = tid; i < D * K; i += nthr) {
         const int d = i / K, j = i - d * K;
         prep[i] = j < k ? -2.0f * cent[j * D + d] : 0.f;
     }
-    if ((int)threadIdx.x < K) {
-        const int j = threadIdx.x;
+    if (tid < K) {
+        const int j = tid;
         float cn = __int_as_float(0x7f800000);  // +inf: padded clusters never win
         if (j < k) {
             double acc = 0.0;
@@ -106,7 +106,7 @@ __global__ void km_init_kernel(const float *__restrict__ feat, size_t img_stride
     for (int i = threadIdx.x; i < k; i += blockDim.x) counts[b * k + i] = 0;
     if (threadIdx.x == 0) done[b] = 0;
     __syncthreads();
-    km_write_prep(c, prep + (size_t)b * (D * K + K), D, k, K);
+    km_write_prep(c, prep + (size_t)b * (D * K + K), D, k, K, threadIdx.x, blockDim.x);
 }
 
 // acc.{lo,hi} = a.{lo,hi} * b + acc.{lo,hi}, each lane one IEEE fp32 FMA (round to nearest even)
@@ -178,20 +178,26 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-constexpr int KM_STAGES = 3;   // ring depth of the phase-A feature pipeline (VEC == 4)
-constexpr int KM_DS = 4;       // feature planes per stage
+#ifndef KM_STAGES_N
+#define KM_STAGES_N 3
+#endif
+#ifndef KM_DS_N
+#define KM_DS_N 4
+#endif
+constexpr int KM_STAGES = KM_STAGES_N;   // ring depth of the phase-A feature pipeline (VEC == 4)
+constexpr int KM_DS = KM_DS_N;           // feature planes per stage
 
-// shared bytes of the phase-B structures: warp bins, transposed slab, changed-pixel list
-__host__ __device__ constexpr size_t km_phase_b_bytes(int K, int tile)
+// shared bytes of the dense phase-B structures (warp bins, transposed slab); they alias the ring
+__host__ __device__ constexpr size_t km_phase_b_bytes(int K)
 {
-    return sizeof(long long) * KM_WARPS * K * 32 + sizeof(int) * 32 * KM_QSTR + (size_t)4 * tile;
+    return sizeof(long long) * KM_WARPS * K * 32 + sizeof(int) * 32 * KM_QSTR;
 }
 __host__ __device__ constexpr size_t km_smem_bytes(int K, int vec, int D)
 {
     const size_t ring = vec == 4 ? sizeof(float) * KM_STAGES * KM_DS * KM_THREADS * 4 : 0;
-    const size_t pb = km_phase_b_bytes(K, KM_THREADS * vec);
+    const size_t pb = km_phase_b_bytes(K);
     const size_t front = ((ring > pb ? ring : pb) + 15) & ~(size_t)15;
-    return front + sizeof(float) * (size_t)((D * K + K + 3) & ~3);
+    return front + (size_t)4 * KM_THREADS * vec + sizeof(float) * (size_t)((D * K + K + 3) & ~3);
 }
 
 template <int K, int VEC>
@@ -201,19 +207,20 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
     constexpr int NACC = K <= 8 ? K : 1;
     constexpr int RING_FLOATS = VEC == 4 ? KM_STAGES * KM_DS * TILE : 0;
     extern __shared__ __align__(128) unsigned char km_smem[];
-    // [ring | (aliased after phase A) s_acc, s_q] [s_m: m [D][K] then cn [K]]
+    // [ring | (aliased by the dense phase-B path) s_acc, s_q] [changed-pixel list] [s_m: m [D][K], cn [K]]
     float *s_ring = reinterpret_cast<float *>(km_smem);
     long long *s_acc = reinterpret_cast<long long *>(km_smem);                                // [warps][K][32]
     int *s_q = reinterpret_cast<int *>(s_acc + KM_WARPS * K * 32);                            // [32][KM_QSTR]
-    unsigned short *s_ent = reinterpret_cast<unsigned short *>(s_q + 32 * KM_QSTR);           // [TILE] changed pixels
+    constexpr size_t PHASE_B_BYTES = km_phase_b_bytes(K);
+    constexpr size_t FRONT_BYTES =
+        ((RING_FLOATS * sizeof(float) > PHASE_B_BYTES ? RING_FLOATS * sizeof(float) : PHASE_B_BYTES) + 15) & ~(size_t)15;
+    unsigned short *s_ent = reinterpret_cast<unsigned short *>(km_smem + FRONT_BYTES);        // [TILE] changed pixels
     unsigned char *s_new = reinterpret_cast<unsigned char *>(s_ent + TILE);                   // [TILE]
     unsigned char *s_old = s_new + TILE;                                                      // [TILE]
-    constexpr size_t PHASE_B_BYTES = km_phase_b_bytes(K, TILE);
-    constexpr size_t FRONT_BYTES = (RING_FLOATS * sizeof(float) > PHASE_B_BYTES ? RING_FLOATS * sizeof(float) : PHASE_B_BYTES);
-    float *s_m = reinterpret_cast<float *>(km_smem + ((FRONT_BYTES + 15) & ~(size_t)15));
+    float *s_m = reinterpret_cast<float *>(km_smem + FRONT_BYTES + 4 * TILE);
     __shared__ __align__(8) unsigned long long s_full[KM_STAGES], s_empty[KM_STAGES];
     __shared__ int s_cnt[K];
-    __shared__ int s_nchg, s_last;
+    __shared__ int s_nchg;
 
     const int b = blockIdx.y;
     const int D = P.D, N = P.N, k = P.k, stride = P.plane_stride;
@@ -222,12 +229,21 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
     const int tile0 = blockIdx.x * TILE;
     float *s_cn = s_m + D * K;
 
-    {
-        const float4 *src = reinterpret_cast<const float4 *>(P.prep + (size_t)b * (D * K + K));
-        float4 *dst = reinterpret_cast<float4 *>(s_m);
-        for (int i = threadIdx.x; i < (D * K + K) / 4; i += KM_THREADS) dst[i] = src[i];
-    }
-    if (threadIdx.x < K) s_cnt[threadIdx.x] = 0;
+    // Feature planes arrive through a KM_STAGES-deep shared-memory ring filled by the TMA engine
+    // (cp.async.bulk, one 4 KB row per plane, completion on an mbarrier): loads of the next
+    // stages are in flight while this one is consumed, at no register cost (VEC == 4 only).
+    const int n_it = (D + KM_DS - 1) / KM_DS;
+    const uint32_t row_bytes = (uint32_t)min(TILE, stride - tile0) * 4u;   // multiple of 16: planes are padded
+    const float *src0 = feat + tile0;
+    auto issue = [&](int it) {   // one elected thread
+        const int s = it % KM_STAGES;
+        const int nd = min(KM_DS, D - it * KM_DS);
+        const uint32_t bar = smem_u32(&s_full[s]);
+        mbar_expect_tx(bar, row_bytes * nd);
+        for (int dd = 0; dd < nd; ++dd)
+            bulk_g2s(smem_u32(s_ring + ((size_t)s * KM_DS + dd) * TILE), src0 + (size_t)(it * KM_DS + dd) * stride,
+                     row_bytes, bar);
+    };
     if (threadIdx.x == 0) {
         s_nchg = 0;
         if constexpr (VEC == 4) {
@@ -236,12 +252,26 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
                 mbar_init(smem_u32(&s_empty[s]), KM_WARPS);
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            // the first stages start flowing before the score table is even loaded
+            for (int it = 0; it < KM_STAGES - 1 && it < n_it; ++it) issue(it);
         }
     }
+    const int p0 = tile0 + threadIdx.x * VEC;
+    unsigned prev = 0xffffffffu;   // labels of the previous iteration (fetched early: needed only after the stream)
+    unsigned char *lab = P.lab8 + (size_t)b * P.lab_stride;
+    if (!P.first) {
+        if (VEC == 4) prev = *reinterpret_cast<const unsigned *>(lab + min(p0, P.lab_stride - 4));
+        else prev = lab[min(p0, N - 1)];
+    }
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(P.prep + (size_t)b * (D * K + K));
+        float4 *dst = reinterpret_cast<float4 *>(s_m);
+        for (int i = threadIdx.x; i < (D * K + K) / 4; i += KM_THREADS) dst[i] = src[i];
+    }
+    if (threadIdx.x < K) s_cnt[threadIdx.x] = 0;
     __syncthreads();
 
     // ---- phase A: scores and labels for VEC consecutive pixels per thread ----
-    const int p0 = tile0 + threadIdx.x * VEC;
     // planes are padded (VEC == 4) so a clamped vector load never leaves the plane
     const int pl = VEC == 4 ? min(p0, stride - VEC) : min(p0, N - 1);
     unsigned long long s2[VEC][K / 2];
@@ -253,23 +283,6 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
         for (int v = 0; v < VEC; ++v) s2[v][i] = c2;
     }
     if constexpr (VEC == 4) {
-        // Feature planes arrive through a KM_STAGES-deep shared-memory ring filled by the TMA
-        // engine (cp.async.bulk, one 4 KB row per plane, completion on an mbarrier): loads of the
-        // next stages are in flight while this one is consumed, at no register cost.
-        const int n_it = (D + KM_DS - 1) / KM_DS;
-        const uint32_t row_bytes = (uint32_t)min(TILE, stride - tile0) * 4u;   // multiple of 16: planes are padded
-        const float *src0 = feat + tile0;
-        auto issue = [&](int it) {   // one elected thread
-            const int s = it % KM_STAGES;
-            const int nd = min(KM_DS, D - it * KM_DS);
-            const uint32_t bar = smem_u32(&s_full[s]);
-            mbar_expect_tx(bar, row_bytes * nd);
-            for (int dd = 0; dd < nd; ++dd)
-                bulk_g2s(smem_u32(s_ring + ((size_t)s * KM_DS + dd) * TILE), src0 + (size_t)(it * KM_DS + dd) * stride,
-                         row_bytes, bar);
-        };
-        if (threadIdx.x == 0)
-            for (int it = 0; it < KM_STAGES - 1 && it < n_it; ++it) issue(it);
         for (int it = 0; it < n_it; ++it) {
             const int s = it % KM_STAGES;
             // refill the stage that was consumed in the previous iteration
@@ -280,28 +293,27 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
             }
             mbar_wait(smem_u32(&s_full[s]), (it / KM_STAGES) & 1);
             const float4 *xrow = reinterpret_cast<const float4 *>(s_ring + (size_t)s * KM_DS * TILE) + threadIdx.x;
+            const ulonglong2 *mrow = reinterpret_cast<const ulonglong2 *>(s_m + (size_t)it * KM_DS * K);
+            auto plane = [&](int dd) {   // one feature plane: 4 pixels x K clusters
+                const float4 t = xrow[dd * (TILE / 4)];
 #pragma unroll
-            for (int dd = 0; dd < KM_DS; ++dd) {
-                const int d = it * KM_DS + dd;
-                if (d < D) {
-                    const float4 t = xrow[dd * (TILE / 4)];
-                    const float x[4] = {t.x, t.y, t.z, t.w};
-                    const ulonglong2 *mrow = reinterpret_cast<const ulonglong2 *>(s_m + d * K);
-#pragma unroll
-                    for (int q = 0; q < K / 4; ++q) {
-                        const ulonglong2 mm = mrow[q];
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) {
-                            ffma2(s2[v][2 * q], mm.x, x[v % 4]);
-                            ffma2(s2[v][2 * q + 1], mm.y, x[v % 4]);
-                        }
-                    }
+                for (int q = 0; q < K / 4; ++q) {
+                    const ulonglong2 mm = mrow[dd * (K / 4) + q];
+                    ffma2(s2[0][2 * q], mm.x, t.x); ffma2(s2[0][2 * q + 1], mm.y, t.x);
+                    ffma2(s2[1 % VEC][2 * q], mm.x, t.y); ffma2(s2[1 % VEC][2 * q + 1], mm.y, t.y);
+                    ffma2(s2[2 % VEC][2 * q], mm.x, t.z); ffma2(s2[2 % VEC][2 * q + 1], mm.y, t.z);
+                    ffma2(s2[3 % VEC][2 * q], mm.x, t.w); ffma2(s2[3 % VEC][2 * q + 1], mm.y, t.w);
                 }
+            };
+            if (it * KM_DS + KM_DS <= D) {   // full stage: no per-plane branches
+#pragma unroll
+                for (int dd = 0; dd < KM_DS; ++dd) plane(dd);
+            } else {
+                for (int dd = 0; dd < D - it * KM_DS; ++dd) plane(dd);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_empty[s]));
         }
-        __syncthreads();   // the ring is reused by phase B
     } else {
         const float *xp = feat + pl;
 #pragma unroll 4
@@ -319,12 +331,6 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
     {
         int newl[VEC], oldl[VEC];
         bool chg[VEC];
-        unsigned prev = 0xffffffffu;
-        unsigned char *lab = P.lab8 + (size_t)b * P.lab_stride;
-        if (!P.first) {
-            if (VEC == 4) prev = *reinterpret_cast<const unsigned *>(lab + min(p0, P.lab_stride - 4));
-            else prev = lab[min(p0, N - 1)];
-        }
         unsigned packed = 0;
         int nchg = 0;
 #pragma unroll
@@ -395,21 +401,11 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
 #else
     const int n_chg = s_nchg;
 #endif
-    if (n_chg > 0 && n_chg <= KM_SPARSE && D * KM_SSTR <= 32 * KM_QSTR) {
-        // sparse: gather every feature of the few changed pixels at once
-        {
-            const int e = lane, g = warp;                       // entry, feature group
-            const int dg = (D + KM_WARPS - 1) / KM_WARPS;
-            if (e < n_chg) {
-                const float *xp = feat + tile0 + s_ent[e];
-                const int d1 = min(D, (g + 1) * dg);
-#pragma unroll 4
-                for (int d = g * dg; d < d1; ++d)
-                    s_q[d * KM_SSTR + e] = __float2int_rn(__ldg(xp + (size_t)d * stride) * P.fix_scale);
-            }
-        }
-        __syncthreads();
-        for (int d = warp * 32 + lane; d < D; d += KM_THREADS) {   // lane = feature: no reduction needed
+    if (n_chg > 0 && n_chg <= KM_SPARSE) {
+        // sparse: lane = feature, so every (cluster, feature) delta lives in exactly one lane and goes
+        // straight from L1/L2 to one global atomic: no shared staging, no barrier, and the warps
+        // beyond ceil(D/32) are already done
+        for (int d = warp * 32 + lane; d < D; d += KM_THREADS) {
             long long acc[NACC];
             long long *bins = s_acc + (size_t)warp * K * 32 + lane;
             if constexpr (K <= 8) {
@@ -418,8 +414,16 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
             } else {
                 for (int j = 0; j < K; ++j) bins[j * 32] = 0;
             }
-            const int *q = s_q + d * KM_SSTR;
-            for (int e = 0; e < n_chg; ++e) km_move<K>(acc, bins, s_new[e], s_old[e], (long long)q[e]);
+            const float *xd = feat + (size_t)d * stride + tile0;
+            for (int e0 = 0; e0 < n_chg; e0 += 8) {
+                float xv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) xv[u] = e0 + u < n_chg ? __ldg(xd + s_ent[e0 + u]) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (e0 + u < n_chg)
+                        km_move<K>(acc, bins, s_new[e0 + u], s_old[e0 + u], (long long)__float2int_rn(xv[u] * P.fix_scale));
+            }
             unsigned long long *dst = reinterpret_cast<unsigned long long *>(P.sums + (size_t)b * k * D + d);
             if constexpr (K <= 8) {
 #pragma unroll
@@ -479,15 +483,21 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
     if (threadIdx.x < k && s_cnt[threadIdx.x]) atomicAdd(P.counts + b * k + threadIdx.x, s_cnt[threadIdx.x]);
 
     // ---- last CTA of this image: sums -> next centroids and next score table ----
-    __threadfence();
+    // The barrier orders every atomic of this CTA before lane 0's fence + ticket (fences are
+    // cumulative); only warp 0 stays for the ticket, so the other warps never wait on its round trip.
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(P.done + b, 1) == P.chunks - 1);
-    __syncthreads();
-    if (!s_last) return;
+    if (warp != 0) return;
+    int last = 0;
+    if (lane == 0) {
+        __threadfence();
+        last = atomicAdd(P.done + b, 1) == P.chunks - 1;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
     __threadfence();
     float *cent = P.cent + (size_t)b * k * D;
     const long long *sums = P.sums + (size_t)b * k * D;
-    for (int i = threadIdx.x; i < k * D; i += KM_THREADS) {
+    for (int i = lane; i < k * D; i += 32) {
         const int j = i / D;
         const int cnt = __ldcg(P.counts + b * k + j);
         if (cnt > 0) {
@@ -495,9 +505,9 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
             cent[i] = __double2float_rn(__ddiv_rn((double)__ldcg(sums + i), den));
         }
     }
-    if (threadIdx.x == 0) P.done[b] = 0;
-    __syncthreads();
-    km_write_prep(cent, P.prep + (size_t)b * (D * K + K), D, k, K);
+    if (lane == 0) P.done[b] = 0;
+    __syncwarp();
+    km_write_prep(cent, P.prep + (size_t)b * (D * K + K), D, k, K, lane, 32);
 }
 
 template <int K, int VEC>

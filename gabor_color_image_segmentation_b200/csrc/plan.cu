@@ -68,7 +68,8 @@ struct gcis_plan {
     uint8_t *d_img = nullptr;
     uint16_t *d_gt = nullptr;
     int32_t *d_n_gt = nullptr, *d_init = nullptr;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     // profiling
     bool profiling = false;
     std::vector<cudaEvent_t> events;  // 5 per group: colour | gabor | kmeans | (metrics: 2 at the end)
@@ -136,6 +137,25 @@ int segment_group(gcis_plan *p, const uint8_t *d_img, int nb, const int32_t *d_i
         if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 3), st);
     }
     return GCIS_OK;
+}
+
+// Segmenter + metrics for `nb` images whose results land at image offset `off` of the plan's
+// result buffers (used by the host entry point to pipeline sub-chunks).
+int pipeline_range(gcis_plan *p, const uint8_t *d_img, const uint16_t *d_gt, const int32_t *d_n_gt,
+                   const int32_t *d_init, int off, int nb, cudaStream_t st, bool)
+{
+    const gcis_config &c = p->cfg;
+    const size_t N = p->N, G = std::max(c.max_gt, 1);
+    int32_t *labels = p->d_labels + (size_t)off * N;
+    for (int b0 = 0; b0 < nb; b0 += p->group) {
+        const int n = std::min(p->group, nb - b0);
+        TRY(segment_group(p, d_img + (size_t)b0 * N * 3, n, d_init + (size_t)b0 * c.k, labels + (size_t)b0 * N, nullptr, st, -1));
+    }
+    return label_metrics_launch(labels, d_gt, d_n_gt, nb, c.height, c.width, c.max_gt, c.k, c.n_lab_cap, c.dil_recall,
+                                p->d_bd_count + off, p->d_gt_counts + (size_t)off * G * GCIS_GT_SLOTS,
+                                p->d_area + (size_t)off * c.k, p->d_perim + (size_t)off * c.k,
+                                p->d_hist + (size_t)off * G * c.k * c.n_lab_cap, p->d_n_seg + off,
+                                p->d_n_lab + (size_t)off * G, p->d_status + off, st);
 }
 
 }  // namespace
@@ -210,7 +230,9 @@ int32_t gcis_plan_create(const gcis_config *cfg, gcis_plan **out)
     p->Np = round_up(p->N, 32);
     int group = cfg->group;
     if (const char *e = getenv("GCIS_GROUP")) group = atoi(e);
-    if (group <= 0) group = 2;
+    // Measured on B200 (profiles/): larger groups fill the machine better and the 126 MB L2 cannot
+    // hold even two images' features across a pass, so the default favours occupancy.
+    if (group <= 0) group = 64;
     p->group = std::min(group, cfg->max_batch);
     size_t smem = 0;
     p->glp = gabor_plan_new(p->bank, H, W, 3, p->P, p->Wp, cfg->feature, &smem);
@@ -264,6 +286,11 @@ void gcis_plan_destroy(gcis_plan *p)
     cudaFree(p->d_hist); cudaFree(p->d_n_seg); cudaFree(p->d_n_lab); cudaFree(p->d_status);
     cudaFree(p->d_img); cudaFree(p->d_gt); cudaFree(p->d_n_gt); cudaFree(p->d_init);
     for (cudaEvent_t e : p->events) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (p->ev_copied[i]) cudaEventDestroy(p->ev_copied[i]);
+        if (p->ev_free[i]) cudaEventDestroy(p->ev_free[i]);
+    }
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     if (p->stream) cudaStreamDestroy(p->stream);
     gabor_plan_delete(p->glp);
     delete p;
@@ -467,26 +494,47 @@ int32_t gcis_pipeline_host(gcis_plan *p, const uint8_t *h_img, const uint16_t *h
     if (!p) return set_error(GCIS_E_INVALID, "null plan");
     if (B < 1) return set_error(GCIS_E_INVALID, "B=%d", B);
     const gcis_config &c = p->cfg;
-    const size_t MB = c.max_batch, G = std::max(c.max_gt, 1), N = p->N;
+    const size_t G = std::max(c.max_gt, 1), N = p->N;
+    // Sub-chunks of one group each travel through two device input buffers: while the compute
+    // stream works on sub-chunk i, the copy stream uploads sub-chunk i+1 (pinned host memory
+    // makes the copies truly asynchronous).
+    const size_t hc = p->group;
     if (!p->d_img) {
-        TRY(dev_alloc(&p->d_img, MB * N * 3, &p->bytes));
-        TRY(dev_alloc(&p->d_gt, MB * G * N, &p->bytes));
-        TRY(dev_alloc(&p->d_n_gt, MB, &p->bytes));
-        TRY(dev_alloc(&p->d_init, MB * c.k, &p->bytes));
+        TRY(dev_alloc(&p->d_img, 2 * hc * N * 3, &p->bytes));
+        TRY(dev_alloc(&p->d_gt, 2 * hc * G * N, &p->bytes));
+        TRY(dev_alloc(&p->d_n_gt, 2 * hc, &p->bytes));
+        TRY(dev_alloc(&p->d_init, 2 * hc * c.k, &p->bytes));
+        GCIS_CUDA_TRY(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            GCIS_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_copied[i], cudaEventDisableTiming));
+            GCIS_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_free[i], cudaEventDisableTiming));
+        }
     }
-    cudaStream_t st = p->stream;
-    for (int b0 = 0; b0 < B; b0 += c.max_batch) {
-        const int nb = std::min<int>(c.max_batch, B - b0);
-        GCIS_CUDA_TRY(cudaMemcpyAsync(p->d_img, h_img + (size_t)b0 * N * 3, (size_t)nb * N * 3, cudaMemcpyHostToDevice, st));
-        if (c.max_gt > 0)
-            GCIS_CUDA_TRY(cudaMemcpyAsync(p->d_gt, h_gt + (size_t)b0 * G * N, sizeof(uint16_t) * nb * G * N, cudaMemcpyHostToDevice, st));
-        if (h_n_gt)
-            GCIS_CUDA_TRY(cudaMemcpyAsync(p->d_n_gt, h_n_gt + b0, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, st));
-        GCIS_CUDA_TRY(cudaMemcpyAsync(p->d_init, h_init_idx + (size_t)b0 * c.k, sizeof(int32_t) * nb * c.k, cudaMemcpyHostToDevice, st));
-        TRY(gcis_pipeline_device(p, p->d_img, p->d_gt, h_n_gt ? p->d_n_gt : nullptr, p->d_init, nb, st));
-        TRY(gcis_pipeline_fetch(p, nb, h_bd_count + b0, h_gt_counts + (size_t)b0 * G * GCIS_GT_SLOTS, h_area + (size_t)b0 * c.k,
-                                h_perim + (size_t)b0 * c.k, h_n_lab + (size_t)b0 * G, h_status + b0,
-                                h_labels ? h_labels + (size_t)b0 * N : nullptr, st));
+    cudaStream_t st = p->stream, cs = p->copy_stream;
+    for (int m0 = 0; m0 < B; m0 += c.max_batch) {          // the result buffers hold max_batch images
+        const int mb = std::min<int>(c.max_batch, B - m0);
+        int i = 0;
+        for (int s0 = 0; s0 < mb; s0 += (int)hc, ++i) {
+            const int nb = std::min<int>((int)hc, mb - s0), buf = i & 1, b0 = m0 + s0;
+            uint8_t *di = p->d_img + (size_t)buf * hc * N * 3;
+            uint16_t *dg = p->d_gt + (size_t)buf * hc * G * N;
+            int32_t *dn = p->d_n_gt + (size_t)buf * hc, *dx = p->d_init + (size_t)buf * hc * c.k;
+            if (i >= 2) GCIS_CUDA_TRY(cudaStreamWaitEvent(cs, p->ev_free[buf], 0));
+            GCIS_CUDA_TRY(cudaMemcpyAsync(di, h_img + (size_t)b0 * N * 3, (size_t)nb * N * 3, cudaMemcpyHostToDevice, cs));
+            if (c.max_gt > 0)
+                GCIS_CUDA_TRY(cudaMemcpyAsync(dg, h_gt + (size_t)b0 * G * N, sizeof(uint16_t) * nb * G * N, cudaMemcpyHostToDevice, cs));
+            if (h_n_gt) GCIS_CUDA_TRY(cudaMemcpyAsync(dn, h_n_gt + b0, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, cs));
+            GCIS_CUDA_TRY(cudaMemcpyAsync(dx, h_init_idx + (size_t)b0 * c.k, sizeof(int32_t) * nb * c.k, cudaMemcpyHostToDevice, cs));
+            GCIS_CUDA_TRY(cudaEventRecord(p->ev_copied[buf], cs));
+            GCIS_CUDA_TRY(cudaStreamWaitEvent(st, p->ev_copied[buf], 0));
+            TRY(pipeline_range(p, di, dg, h_n_gt ? dn : nullptr, dx, s0, nb, st, false));
+            GCIS_CUDA_TRY(cudaEventRecord(p->ev_free[buf], st));
+        }
+        TRY(gcis_pipeline_fetch(p, mb, h_bd_count + m0, h_gt_counts + (size_t)m0 * G * GCIS_GT_SLOTS, h_area + (size_t)m0 * c.k,
+                                h_perim + (size_t)m0 * c.k, h_n_lab + (size_t)m0 * G, h_status + m0,
+                                h_labels ? h_labels + (size_t)m0 * N : nullptr, st));
+        // both input buffers are idle again before the next block reuses them from index 0
+        GCIS_CUDA_TRY(cudaStreamSynchronize(cs));
     }
     return GCIS_OK;
 }

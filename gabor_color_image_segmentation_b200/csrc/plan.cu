@@ -57,9 +57,14 @@ struct gcis_plan {
     // device workspaces
     float *d_taps = nullptr;
     GaborScale *d_scales = nullptr;
-    float *d_planes = nullptr;   // [group][3][H][Wp]
-    float *d_feat = nullptr;     // [group][D][N]
-    void *d_km_ws = nullptr;
+    // Two "lanes" of per-group workspaces: group g runs on lane g & 1, so the FP32-bound Gabor
+    // kernel of one group overlaps the HBM-bound k-means passes of the previous one.
+    float *d_planes[2] = {nullptr, nullptr};   // [group][3][H][Wp]
+    float *d_feat[2] = {nullptr, nullptr};     // [group][D][Np]
+    void *d_km_ws[2] = {nullptr, nullptr};
+    cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    cudaEvent_t lane_done[2] = {nullptr, nullptr}, ev_fork = nullptr;
+    int n_lanes = 1;
     int32_t *d_labels = nullptr; // [max_batch][N]
     int64_t *d_bd_count = nullptr, *d_gt_counts = nullptr;
     int32_t *d_area = nullptr, *d_perim = nullptr, *d_hist = nullptr, *d_n_seg = nullptr, *d_n_lab = nullptr,
@@ -117,23 +122,23 @@ cudaEvent_t plan_event(gcis_plan *p, size_t i)
 }
 
 // colour -> Gabor -> k-means for one group of images whose features live in plan->d_feat.
-int segment_group(gcis_plan *p, const uint8_t *d_img, int nb, const int32_t *d_init, int32_t *d_labels,
+int segment_group(gcis_plan *p, int lane, const uint8_t *d_img, int nb, const int32_t *d_init, int32_t *d_labels,
                   float *d_feat_out, cudaStream_t st, int group_index)
 {
     const gcis_config &c = p->cfg;
     // the plan's own feature buffer pads every plane to Np floats so the k-means pass can use
     // aligned 128-bit loads; a caller-supplied tensor is dense [D][H][W]
-    float *feat = d_feat_out ? d_feat_out : p->d_feat;
+    float *feat = d_feat_out ? d_feat_out : p->d_feat[lane];
     const int pstride = d_feat_out ? p->N : p->Np;
     const bool prof = p->profiling && group_index >= 0;
     if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 0), st);
-    TRY(colour_planes_launch(d_img, p->d_planes, nb, c.height, c.width, p->P, p->Wp, c.colour_space, st));
+    TRY(colour_planes_launch(d_img, p->d_planes[lane], nb, c.height, c.width, p->P, p->Wp, c.colour_space, st));
     if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 1), st);
-    TRY(gabor_launch(*p->glp, p->d_planes, feat, p->d_taps, p->d_scales, nb, pstride, st));
+    TRY(gabor_launch(*p->glp, p->d_planes[lane], feat, p->d_taps, p->d_scales, nb, pstride, st));
     if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 2), st);
     if (d_labels) {
         TRY(kmeans_launch(feat, (size_t)p->D * pstride, pstride, nb, p->D, p->N, c.k, c.iters, c.fix_shift, d_init,
-                          d_labels, nullptr, p->d_km_ws, st));
+                          d_labels, nullptr, p->d_km_ws[lane], st));
         if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 3), st);
     }
     return GCIS_OK;
@@ -141,15 +146,15 @@ int segment_group(gcis_plan *p, const uint8_t *d_img, int nb, const int32_t *d_i
 
 // Segmenter + metrics for `nb` images whose results land at image offset `off` of the plan's
 // result buffers (used by the host entry point to pipeline sub-chunks).
-int pipeline_range(gcis_plan *p, const uint8_t *d_img, const uint16_t *d_gt, const int32_t *d_n_gt,
-                   const int32_t *d_init, int off, int nb, cudaStream_t st, bool)
+int pipeline_range(gcis_plan *p, int lane, const uint8_t *d_img, const uint16_t *d_gt, const int32_t *d_n_gt,
+                   const int32_t *d_init, int off, int nb, cudaStream_t st)
 {
     const gcis_config &c = p->cfg;
     const size_t N = p->N, G = std::max(c.max_gt, 1);
     int32_t *labels = p->d_labels + (size_t)off * N;
     for (int b0 = 0; b0 < nb; b0 += p->group) {
         const int n = std::min(p->group, nb - b0);
-        TRY(segment_group(p, d_img + (size_t)b0 * N * 3, n, d_init + (size_t)b0 * c.k, labels + (size_t)b0 * N, nullptr, st, -1));
+        TRY(segment_group(p, lane, d_img + (size_t)b0 * N * 3, n, d_init + (size_t)b0 * c.k, labels + (size_t)b0 * N, nullptr, st, -1));
     }
     return label_metrics_launch(labels, d_gt, d_n_gt, nb, c.height, c.width, c.max_gt, c.k, c.n_lab_cap, c.dil_recall,
                                 p->d_bd_count + off, p->d_gt_counts + (size_t)off * G * GCIS_GT_SLOTS,
@@ -247,13 +252,16 @@ int32_t gcis_plan_create(const gcis_config *cfg, gcis_plan **out)
     } while (0)
     PA(p->d_taps, p->bank.taps.size());
     PA(p->d_scales, p->bank.scales.size());
-    PA(p->d_planes, (size_t)p->group * 3 * H * p->Wp);
-    PA(p->d_feat, (size_t)p->group * p->D * p->Np);
-    {
+    p->n_lanes = 2;
+    if (const char *e = getenv("GCIS_LANES")) p->n_lanes = atoi(e) >= 2 ? 2 : 1;
+    if (cfg->max_batch <= p->group) p->n_lanes = 1;
+    for (int l = 0; l < p->n_lanes; ++l) {
+        PA(p->d_planes[l], (size_t)p->group * 3 * H * p->Wp);
+        PA(p->d_feat[l], (size_t)p->group * p->D * p->Np);
         char *ws = nullptr;
         int rc2 = dev_alloc(&ws, kmeans_workspace_bytes(p->group, p->D, p->N, cfg->k), &p->bytes);
         if (rc2) return fail(rc2);
-        p->d_km_ws = ws;
+        p->d_km_ws[l] = ws;
     }
     PA(p->d_labels, MB * p->N);
     PA(p->d_bd_count, MB);
@@ -270,6 +278,16 @@ int32_t gcis_plan_create(const gcis_config *cfg, gcis_plan **out)
         set_error(GCIS_E_CUDA, "plan: uploading the bank failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(GCIS_E_CUDA);
     }
+    for (int l = 0; l < p->n_lanes; ++l)
+        if (cudaStreamCreateWithFlags(&p->lane_stream[l], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->lane_done[l], cudaEventDisableTiming) != cudaSuccess) {
+            set_error(GCIS_E_CUDA, "plan: lane stream/event creation failed");
+            return fail(GCIS_E_CUDA);
+        }
+    if (cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
+        set_error(GCIS_E_CUDA, "plan: cudaEventCreate failed");
+        return fail(GCIS_E_CUDA);
+    }
     if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) {
         set_error(GCIS_E_CUDA, "plan: cudaStreamCreate failed");
         return fail(GCIS_E_CUDA);
@@ -281,7 +299,13 @@ int32_t gcis_plan_create(const gcis_config *cfg, gcis_plan **out)
 void gcis_plan_destroy(gcis_plan *p)
 {
     if (!p) return;
-    cudaFree(p->d_taps); cudaFree(p->d_scales); cudaFree(p->d_planes); cudaFree(p->d_feat); cudaFree(p->d_km_ws);
+    cudaFree(p->d_taps); cudaFree(p->d_scales);
+    for (int l = 0; l < 2; ++l) {
+        cudaFree(p->d_planes[l]); cudaFree(p->d_feat[l]); cudaFree(p->d_km_ws[l]);
+        if (p->lane_done[l]) cudaEventDestroy(p->lane_done[l]);
+        if (p->lane_stream[l]) cudaStreamDestroy(p->lane_stream[l]);
+    }
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     cudaFree(p->d_labels); cudaFree(p->d_bd_count); cudaFree(p->d_gt_counts); cudaFree(p->d_area); cudaFree(p->d_perim);
     cudaFree(p->d_hist); cudaFree(p->d_n_seg); cudaFree(p->d_n_lab); cudaFree(p->d_status);
     cudaFree(p->d_img); cudaFree(p->d_gt); cudaFree(p->d_n_gt); cudaFree(p->d_init);
@@ -320,7 +344,7 @@ int32_t gcis_gabor_features(gcis_plan *p, const uint8_t *d_img, int32_t B, float
     const size_t img_stride = (size_t)p->N * 3, feat_stride = (size_t)p->D * p->N;
     for (int b0 = 0; b0 < B; b0 += p->group) {
         const int nb = std::min(p->group, B - b0);
-        TRY(segment_group(p, d_img + b0 * img_stride, nb, nullptr, nullptr, d_feat + b0 * feat_stride, st, -1));
+        TRY(segment_group(p, 0, d_img + b0 * img_stride, nb, nullptr, nullptr, d_feat + b0 * feat_stride, st, -1));
     }
     return GCIS_OK;
 }
@@ -336,7 +360,7 @@ int32_t gcis_kmeans(gcis_plan *p, const float *d_feat, int32_t B, const int32_t 
         const int nb = std::min(p->group, B - b0);
         TRY(kmeans_launch(d_feat + b0 * feat_stride, feat_stride, p->N, nb, p->D, p->N, c.k, c.iters, c.fix_shift, d_init_idx + (size_t)b0 * c.k,
                           d_labels + (size_t)b0 * p->N, d_centroids ? d_centroids + (size_t)b0 * c.k * p->D : nullptr,
-                          p->d_km_ws, st));
+                          p->d_km_ws[0], st));
     }
     return GCIS_OK;
 }
@@ -347,12 +371,23 @@ int32_t gcis_segment_device(gcis_plan *p, const uint8_t *d_img, int32_t B, const
     TRY(plan_check_batch(p, B));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t img_stride = (size_t)p->N * 3;
+    const bool lanes = p->n_lanes == 2 && B > p->group;
+    if (lanes) {   // fork: both lanes start after everything already queued on the caller's stream
+        GCIS_CUDA_TRY(cudaEventRecord(p->ev_fork, st));
+        for (int l = 0; l < 2; ++l) GCIS_CUDA_TRY(cudaStreamWaitEvent(p->lane_stream[l], p->ev_fork, 0));
+    }
     int gi = 0;
     for (int b0 = 0; b0 < B; b0 += p->group, ++gi) {
         const int nb = std::min(p->group, B - b0);
-        TRY(segment_group(p, d_img + b0 * img_stride, nb, d_init_idx + (size_t)b0 * p->cfg.k, d_labels + (size_t)b0 * p->N,
-                          nullptr, st, gi));
+        const int lane = lanes ? (gi & 1) : 0;
+        TRY(segment_group(p, lane, d_img + b0 * img_stride, nb, d_init_idx + (size_t)b0 * p->cfg.k,
+                          d_labels + (size_t)b0 * p->N, nullptr, lanes ? p->lane_stream[lane] : st, gi));
     }
+    if (lanes)     // join
+        for (int l = 0; l < 2; ++l) {
+            GCIS_CUDA_TRY(cudaEventRecord(p->lane_done[l], p->lane_stream[l]));
+            GCIS_CUDA_TRY(cudaStreamWaitEvent(st, p->lane_done[l], 0));
+        }
     p->n_groups_last = gi;
     return GCIS_OK;
 }
@@ -511,6 +546,7 @@ int32_t gcis_pipeline_host(gcis_plan *p, const uint8_t *h_img, const uint16_t *h
         }
     }
     cudaStream_t st = p->stream, cs = p->copy_stream;
+    const bool lanes = p->n_lanes == 2;
     for (int m0 = 0; m0 < B; m0 += c.max_batch) {          // the result buffers hold max_batch images
         const int mb = std::min<int>(c.max_batch, B - m0);
         int i = 0;
@@ -526,10 +562,16 @@ int32_t gcis_pipeline_host(gcis_plan *p, const uint8_t *h_img, const uint16_t *h
             if (h_n_gt) GCIS_CUDA_TRY(cudaMemcpyAsync(dn, h_n_gt + b0, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, cs));
             GCIS_CUDA_TRY(cudaMemcpyAsync(dx, h_init_idx + (size_t)b0 * c.k, sizeof(int32_t) * nb * c.k, cudaMemcpyHostToDevice, cs));
             GCIS_CUDA_TRY(cudaEventRecord(p->ev_copied[buf], cs));
-            GCIS_CUDA_TRY(cudaStreamWaitEvent(st, p->ev_copied[buf], 0));
-            TRY(pipeline_range(p, di, dg, h_n_gt ? dn : nullptr, dx, s0, nb, st, false));
-            GCIS_CUDA_TRY(cudaEventRecord(p->ev_free[buf], st));
+            cudaStream_t ls = lanes ? p->lane_stream[buf] : st;
+            GCIS_CUDA_TRY(cudaStreamWaitEvent(ls, p->ev_copied[buf], 0));
+            TRY(pipeline_range(p, lanes ? buf : 0, di, dg, h_n_gt ? dn : nullptr, dx, s0, nb, ls));
+            GCIS_CUDA_TRY(cudaEventRecord(p->ev_free[buf], ls));
         }
+        if (lanes)
+            for (int l = 0; l < 2; ++l) {
+                GCIS_CUDA_TRY(cudaEventRecord(p->lane_done[l], p->lane_stream[l]));
+                GCIS_CUDA_TRY(cudaStreamWaitEvent(st, p->lane_done[l], 0));
+            }
         TRY(gcis_pipeline_fetch(p, mb, h_bd_count + m0, h_gt_counts + (size_t)m0 * G * GCIS_GT_SLOTS, h_area + (size_t)m0 * c.k,
                                 h_perim + (size_t)m0 * c.k, h_n_lab + (size_t)m0 * G, h_status + m0,
                                 h_labels ? h_labels + (size_t)m0 * N : nullptr, st));

@@ -495,19 +495,30 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
     __threadfence();
+    // This warp is the image's serial tail of the pass, so keep it short: independent loads are
+    // batched, and the new centroids are staged in shared memory (the score table is no longer
+    // needed: every other warp of this CTA has left) for the table rebuild.
     float *cent = P.cent + (size_t)b * k * D;
     const long long *sums = P.sums + (size_t)b * k * D;
-    for (int i = lane; i < k * D; i += 32) {
-        const int j = i / D;
-        const int cnt = __ldcg(P.counts + b * k + j);
-        if (cnt > 0) {
-            const double den = __dmul_rn((double)cnt, (double)P.fix_scale);
-            cent[i] = __double2float_rn(__ddiv_rn((double)__ldcg(sums + i), den));
+    float *s_c = s_m;
+    const int my_cnt = lane < k ? __ldcg(P.counts + b * k + lane) : 0;
+#pragma unroll 4
+    for (int i0 = 0; i0 < k * D; i0 += 32) {
+        const int i = i0 + lane;
+        const bool ok = i < k * D;
+        const int cnt = __shfl_sync(0xffffffffu, my_cnt, ok ? i / D : 0);
+        if (ok) {
+            const long long s = __ldcg(sums + i);
+            float c;
+            if (cnt > 0) c = __double2float_rn(__ddiv_rn((double)s, __dmul_rn((double)cnt, (double)P.fix_scale)));
+            else c = cent[i];
+            cent[i] = c;
+            s_c[i] = c;
         }
     }
     if (lane == 0) P.done[b] = 0;
     __syncwarp();
-    km_write_prep(cent, P.prep + (size_t)b * (D * K + K), D, k, K, lane, 32);
+    km_write_prep(s_c, P.prep + (size_t)b * (D * K + K), D, k, K, lane, 32);
 }
 
 template <int K, int VEC>

@@ -12,7 +12,8 @@ from .groundtruth import get_segmentation, get_segment_from_filename, pack_groun
 from .metrics import metrics, finish_image, find_boundaries
 from .engine import GaborBank, Plan, BatchCounts, kmeans_init_indices, label_counts_host
 from .segment import gabor_kmeans_segment
+from .region_scores import region_scores
 
 __all__ = ["metrics", "get_segmentation", "get_segment_from_filename", "gabor_kmeans_segment",
            "GaborBank", "Plan", "BatchCounts", "kmeans_init_indices", "label_counts_host",
-           "pack_ground_truths", "finish_image", "find_boundaries"]
+           "pack_ground_truths", "finish_image", "find_boundaries", "region_scores"]

@@ -76,6 +76,7 @@ SIGNATURES = {
     "gcis_find_boundaries_host": (_i32, [_vp, _i32, _i32, _i32, _vp]),
     "gcis_pipeline_device": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "gcis_pipeline_fetch": (_i32, [_vp, _i32] + [_vp] * 7 + [_vp]),
+    "gcis_pipeline_fetch_hist": (_i32, [_vp, _i32, _vp, _vp]),
     "gcis_pipeline_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32] + [_vp] * 7),
     "gcis_plan_set_profiling": (_i32, [_vp, _i32]),
     "gcis_plan_last_stage_ms": (_i32, [_vp, _vp]),

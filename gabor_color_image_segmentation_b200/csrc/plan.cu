@@ -522,6 +522,18 @@ int32_t gcis_pipeline_fetch(gcis_plan *p, int32_t B, int64_t *h_bd_count, int64_
     return GCIS_OK;
 }
 
+int32_t gcis_pipeline_fetch_hist(gcis_plan *p, int32_t B, int32_t *h_hist, void *stream)
+{
+    TRY(plan_check_batch(p, B));
+    if (!h_hist) return set_error(GCIS_E_INVALID, "null h_hist");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const gcis_config &c = p->cfg;
+    const size_t n = (size_t)B * std::max(c.max_gt, 1) * c.k * c.n_lab_cap;
+    GCIS_CUDA_TRY(cudaMemcpyAsync(h_hist, p->d_hist, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    GCIS_CUDA_TRY(cudaStreamSynchronize(st));
+    return GCIS_OK;
+}
+
 int32_t gcis_pipeline_host(gcis_plan *p, const uint8_t *h_img, const uint16_t *h_gt, const int32_t *h_n_gt,
                            const int32_t *h_init_idx, int32_t B, int64_t *h_bd_count, int64_t *h_gt_counts,
                            int32_t *h_area, int32_t *h_perim, int32_t *h_n_lab, int32_t *h_status, int32_t *h_labels)

@@ -193,6 +193,13 @@ class Plan:
                    "gcis_pipeline_fetch")
         return self._counts(o, B, ng.cpu().numpy() if ng is not None else None)
 
+    def fetch_hist(self, B: int) -> np.ndarray:
+        """Contingency tables [B,G,k,n_lab_cap] int32 of the last pipeline call (up to max_batch images)."""
+        h = np.zeros((B, max(self.max_gt, 1), self.k, self.n_lab_cap), np.int32)
+        _lib.check(self.lib.gcis_pipeline_fetch_hist(self._h, B, h.ctypes.data, self._stream()),
+                   "gcis_pipeline_fetch_hist")
+        return h
+
     def pipeline_host(self, img_ptr, gt_ptr, init_ptr, B: int, n_gt: Optional[np.ndarray] = None,
                       want_labels: bool = False) -> BatchCounts:
         """Host buffers in, host records out (copies inside).  *_ptr: objects with a host address —

@@ -180,6 +180,10 @@ GCIS_API int32_t gcis_pipeline_fetch(gcis_plan *plan, int32_t B, int64_t *h_bd_c
                             int32_t *h_area, int32_t *h_perim, int32_t *h_n_lab, int32_t *h_status,
                             int32_t *h_labels, void *stream);
 
+/* Contingency tables of the last pipeline call (metrics.py:115-126), [B][G][k][n_lab_cap] int32:
+ * the input of the region scores that go beyond the reference (PRI, VoI, covering). */
+GCIS_API int32_t gcis_pipeline_fetch_hist(gcis_plan *plan, int32_t B, int32_t *h_hist, void *stream);
+
 /* ---- whole path, host buffers (bench `e2e`; script.py:22-38 for a batch) ----
  * h_img [B][H][W][3] uint8, h_gt [B][G][H][W] uint16, h_n_gt [B] or NULL,
  * h_init_idx [B][k].  B may exceed max_batch; the call streams chunks of

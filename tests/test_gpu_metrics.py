@@ -160,3 +160,33 @@ def test_full_size_properties():
     # batch invariance
     one = label_counts_host(lbs[2:3], gts[2:3])
     np.testing.assert_array_equal(one.gt_counts[0], c.gt_counts[2])
+
+
+def test_region_scores_from_gpu_tables_against_sklearn():
+    """PRI / VoI / covering (beyond the reference, builder-defined) from the GPU contingency tables,
+    checked against scikit-learn's pair-counting and information scores on the label maps."""
+    from sklearn.metrics import mutual_info_score, rand_score
+    from gabor_color_image_segmentation_b200 import label_counts_host
+    from gabor_color_image_segmentation_b200.region_scores import region_scores
+    rng = np.random.default_rng(17)
+    B, H, W, G = 2, 90, 120, 3
+    lbs = np.stack([_voronoi(rng, H, W, 7) for _ in range(B)])
+    gts = np.stack([np.stack([_voronoi(rng, H, W, 6, base=1) for _ in range(G)]) for _ in range(B)]).astype(np.uint16)
+    c = label_counts_host(lbs, gts, want_hist=True)
+    s = region_scores(c.hist)
+    for b in range(B):
+        ri, voi, cov = [], [], []
+        for g in range(G):
+            x, y = lbs[b].ravel(), gts[b, g].ravel().astype(np.int64)
+            ri.append(rand_score(y, x))
+            hx = mutual_info_score(x, x); hy = mutual_info_score(y, y); mi = mutual_info_score(x, y)
+            voi.append((hx + hy - 2 * mi) / np.log(2))
+            acc = 0.0
+            for j in np.unique(y):
+                m = y == j
+                best = max(((x == i) & m).sum() / ((x == i) | m).sum() for i in np.unique(x[m]))
+                acc += m.sum() * best
+            cov.append(acc / x.size)
+        assert abs(s["pri"][b] - np.mean(ri)) < 1e-12
+        assert abs(s["voi"][b] - np.mean(voi)) < 1e-9
+        assert abs(s["covering"][b] - np.mean(cov)) < 1e-12

@@ -187,10 +187,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 constexpr int KM_STAGES = KM_STAGES_N;   // ring depth of the phase-A feature pipeline (VEC == 4)
 constexpr int KM_DS = KM_DS_N;           // feature planes per stage
 
-// shared bytes of the dense phase-B structures (warp bins, transposed slab); they alias the ring
+constexpr int KM_BCOLS = 128;                // dense path: 32 features x 4 byte digits per slab
+constexpr int KM_BSTR = KM_ROUND / 4 + 4;    // words per digit column (4 entries per word), padded: conflict-free
+
+// shared bytes of the phase-B structures (warp bins of the sparse path for K > 8, digit slab of
+// the dense path); they alias the ring
 __host__ __device__ constexpr size_t km_phase_b_bytes(int K)
 {
-    return sizeof(long long) * KM_WARPS * K * 32 + sizeof(int) * 32 * KM_QSTR;
+    return sizeof(long long) * KM_WARPS * K * 32 + sizeof(int) * KM_BCOLS * KM_BSTR;
 }
 __host__ __device__ constexpr size_t km_smem_bytes(int K, int vec, int D)
 {
@@ -435,49 +439,104 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
             }
         }
     } else if (n_chg > 0) {
+        // Dense: the per-cluster sums are a small integer GEMM, so they run on the tensor cores and stay
+        // exact:  S[j][d] += sum_e A[j][e] * q'[e][d]  with A[j][e] = [new_e = j] - [old_e = j] (int8) and
+        // q' = q + 2^31 split into four unsigned byte digits (mma.sync m16n8k32 s8 x u8 -> s32).  The
+        // 2^31 offset is removed with the cluster's population delta: sum_e A[j][e] = s_cnt[j].
+        const int n_pad = (n_chg + KM_ROUND - 1) / KM_ROUND * KM_ROUND;
+        for (int i = n_chg + threadIdx.x; i < n_pad; i += KM_THREADS) { s_new[i] = KM_NONE; s_old[i] = KM_NONE; }
+        __syncthreads();   // padding visible; from here on every warp only touches its own 16 digit columns
+        unsigned *s_b = reinterpret_cast<unsigned *>(s_q);   // [KM_BCOLS][KM_BSTR]: column (feature, digit), word = 4 entries
+        constexpr int MT = (K + 15) / 16;
+        const int g = lane >> 2, kq = lane & 3;
         for (int d0 = 0; d0 < D; d0 += 32) {
             const int nd = min(32, D - d0);
-            long long acc[NACC];
-            long long *bins = s_acc + (size_t)warp * K * 32 + lane;
-            if constexpr (K <= 8) {
+            int c[MT][2][4];
 #pragma unroll
-                for (int j = 0; j < NACC; ++j) acc[j] = 0;
-            } else {
-                for (int j = 0; j < K; ++j) bins[j * 32] = 0;
-            }
-            for (int r0 = 0; r0 < n_chg; r0 += KM_ROUND) {
-                __syncthreads();  // slab free
-                const int cnt = min(KM_ROUND, n_chg - r0);
-                if ((int)threadIdx.x < cnt) {
-                    const float *xp = feat + (size_t)d0 * stride + tile0 + s_ent[r0 + threadIdx.x];
-#pragma unroll 8
-                    for (int dd = 0; dd < nd; ++dd)
-                        s_q[dd * KM_QSTR + threadIdx.x] = __float2int_rn(__ldg(xp + (size_t)dd * stride) * P.fix_scale);
-                }
-                __syncthreads();
-                const int e0 = warp * 32, e1 = min(e0 + 32, cnt);
-                if (lane < nd) {
-                    const int *q = s_q + lane * KM_QSTR;
-                    for (int e = e0; e < e1; ++e) km_move<K>(acc, bins, s_new[r0 + e], s_old[r0 + e], (long long)q[e]);
-                }
-            }
-            if constexpr (K <= 8) {
+            for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                for (int j = 0; j < NACC; ++j) bins[j * 32] = acc[j];
-            }
-            __syncthreads();
-            // reduce the warp-private bins and publish: one global atomic per (cluster, feature) per CTA
-            for (int i = threadIdx.x; i < K * 32; i += KM_THREADS) {
-                const int j = i >> 5, dl = i & 31;
-                if (j < k && dl < nd) {
-                    long long v = 0;
+                for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-                    for (int w = 0; w < KM_WARPS; ++w) v += s_acc[(size_t)w * K * 32 + i];
-                    if (v) atomicAdd(reinterpret_cast<unsigned long long *>(P.sums + ((size_t)b * k + j) * D + d0 + dl),
-                                     (unsigned long long)v);
+                    for (int i = 0; i < 4; ++i) c[mt][nt][i] = 0;
+            for (int r0 = 0; r0 < n_pad; r0 += KM_ROUND) {
+                __syncwarp();  // this warp's columns are free again
+                {   // stage: thread = 4 consecutive entries x 4 features (the warp's own); bytes transposed in registers
+                    const int eq = threadIdx.x & 31, fg = threadIdx.x >> 5;
+                    const float *xp[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = r0 + eq * 4 + u;
+                        ok[u] = e < n_chg;
+                        xp[u] = feat + (size_t)d0 * stride + tile0 + (ok[u] ? (int)s_ent[e] : 0);
+                    }
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        const int dd = fg * 4 + f;
+                        unsigned q[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            q[u] = (dd < nd && ok[u])
+                                       ? ((unsigned)__float2int_rn(__ldg(xp[u] + (size_t)dd * stride) * P.fix_scale) ^ 0x80000000u)
+                                       : 0u;
+                        const unsigned t0 = __byte_perm(q[0], q[1], 0x5140), t1 = __byte_perm(q[2], q[3], 0x5140);
+                        const unsigned t2 = __byte_perm(q[0], q[1], 0x7362), t3 = __byte_perm(q[2], q[3], 0x7362);
+                        unsigned *dst = s_b + (dd * 4) * KM_BSTR + eq;
+                        dst[0 * KM_BSTR] = __byte_perm(t0, t1, 0x5410);
+                        dst[1 * KM_BSTR] = __byte_perm(t0, t1, 0x7632);
+                        dst[2 * KM_BSTR] = __byte_perm(t2, t3, 0x5410);
+                        dst[3 * KM_BSTR] = __byte_perm(t2, t3, 0x7632);
+                    }
+                }
+                __syncwarp();
+                // warp w owns digit columns 16w .. 16w+15 (features 4w .. 4w+3 of the slab)
+                const unsigned *newp = reinterpret_cast<const unsigned *>(s_new + r0);
+                const unsigned *oldp = reinterpret_cast<const unsigned *>(s_old + r0);
+#pragma unroll
+                for (int ks = 0; ks < KM_ROUND / 32; ++ks) {
+                    const unsigned n0 = newp[ks * 8 + kq], n1 = newp[ks * 8 + 4 + kq];
+                    const unsigned o0 = oldp[ks * 8 + kq], o1 = oldp[ks * 8 + 4 + kq];
+                    unsigned bf[2][2];
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const unsigned *col = s_b + ((2 * warp + nt) * 8 + g) * KM_BSTR + ks * 8 + kq;
+                        bf[nt][0] = col[0];
+                        bf[nt][1] = col[4];
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const unsigned r0w = (unsigned)(mt * 16 + g) * 0x01010101u, r1w = r0w + 0x08080808u;
+                        const unsigned a0 = (__vcmpeq4(n0, r0w) & 0x01010101u) | __vcmpeq4(o0, r0w);
+                        const unsigned a1 = (__vcmpeq4(n0, r1w) & 0x01010101u) | __vcmpeq4(o0, r1w);
+                        const unsigned a2 = (__vcmpeq4(n1, r0w) & 0x01010101u) | __vcmpeq4(o1, r0w);
+                        const unsigned a3 = (__vcmpeq4(n1, r1w) & 0x01010101u) | __vcmpeq4(o1, r1w);
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt)
+                            asm volatile(
+                                "mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                : "+r"(c[mt][nt][0]), "+r"(c[mt][nt][1]), "+r"(c[mt][nt][2]), "+r"(c[mt][nt][3])
+                                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf[nt][0]), "r"(bf[nt][1]));
+                    }
                 }
             }
-            __syncthreads();  // bins are re-zeroed by the next slab
+            // digits -> int64, remove the offset, publish: one global atomic per (cluster, feature) per CTA
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int hrow = 0; hrow < 2; ++hrow) {
+                        long long part = (long long)c[mt][nt][2 * hrow] + ((long long)c[mt][nt][2 * hrow + 1] << 8);
+                        if (kq & 1) part <<= 16;
+                        part += __shfl_xor_sync(0xffffffffu, part, 1);
+                        const int j = mt * 16 + hrow * 8 + g;
+                        const int d = d0 + (2 * warp + nt) * 2 + (kq >> 1);
+                        if (!(kq & 1) && j < k && d < D) {
+                            const long long v = part - ((long long)s_cnt[j] << 31);
+                            if (v) atomicAdd(reinterpret_cast<unsigned long long *>(P.sums + ((size_t)b * k + j) * D + d),
+                                             (unsigned long long)v);
+                        }
+                    }
         }
     }
     if (threadIdx.x < k && s_cnt[threadIdx.x]) atomicAdd(P.counts + b * k + threadIdx.x, s_cnt[threadIdx.x]);

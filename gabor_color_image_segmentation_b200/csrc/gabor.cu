@@ -197,7 +197,7 @@ struct GaborParams {
     int first_block[GB_MAX_SCALES + 1];  // block ranges ordered from the widest scale to the narrowest
     int order[GB_MAX_SCALES];    // scale handled by range i
     int nsrc_cap;                // rows of T the shared buffer holds
-    int istr;                    // chunk row stride (odd)
+    int istr;                    // chunk row stride: 32 n + 4 floats (aligned, conflict-free 128-bit row loads)
     int tap_slot;                // floats reserved per staged filter (complex, interleaved) in shared memory
     int rowtab_cap;
 };
@@ -229,7 +229,8 @@ __device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi)
 //  !CT && !CX: S[i] = A      += w*x
 // w0 points at the window of block 0; the window moves down by R taps per block.
 template <int R, bool CT, bool CX, class XLoad>
-__device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u64 (&P)[R], u64 (&Q)[R], float (&S)[R])
+__device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u64 (&P)[R], u64 (&Q)[R], float (&S)[R],
+                                      const float *xvec = nullptr)
 {
 #pragma unroll 1
     for (int m = 0; m < nblk; ++m) {
@@ -252,8 +253,13 @@ __device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u6
         }
         float xr[R], xi[R];
         u64 xp[R];
+        if (R == 4 && !CX && xvec) {   // row pass: the R inputs of a block are one aligned 128-bit load
+            const float4 v = *reinterpret_cast<const float4 *>(xvec + m * 4);
+            xr[0] = v.x; xr[1 % R] = v.y; xr[2 % R] = v.z; xr[3 % R] = v.w;
+        } else {
 #pragma unroll
-        for (int uu = 0; uu < R; ++uu) xload(m * R + uu, xr[uu], xi[uu], xp[uu]);
+            for (int uu = 0; uu < R; ++uu) xload(m * R + uu, xr[uu], xi[uu], xp[uu]);
+        }
 #pragma unroll
         for (int uu = 0; uu < R; ++uu) {
 #pragma unroll
@@ -285,7 +291,7 @@ __device__ __forceinline__ void row_pass_chunk(const float *chunk, int istr, con
     for (int i = 0; i < GB_RR; ++i) { Pv[i] = 0ull; Qv[i] = 0ull; Sv[i] = 0.f; }
     const float *src = chunk + lane * istr + xb;
     sweep<GB_RR, CT, false>([&](int u, float &xr, float &xi, u64 &xp) { xr = src[u]; xi = 0.f; xp = 0ull; }, w0, nblk, Pv,
-                            Qv, Sv);
+                            Qv, Sv, GB_RR == 4 ? src : nullptr);
     if (active) {
         u64 *dst = reinterpret_cast<u64 *>(T + (size_t)trow * GB_TWP + xb);
 #pragma unroll
@@ -390,8 +396,8 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
     float *tap_row = smem;                       // first, so the 128-bit tap loads stay 16-byte aligned
     float *tap_col = tap_row + P.tap_slot;
     int *rowtab = reinterpret_cast<int *>(tap_col + P.tap_slot);
-    float2 *T = reinterpret_cast<float2 *>(rowtab + P.rowtab_cap);   // [nsrc_cap][GB_TWP] complex row-pass output
-    float *chunk = reinterpret_cast<float *>(T + (size_t)P.nsrc_cap * GB_TWP);
+    float *chunk = reinterpret_cast<float *>(rowtab + P.rowtab_cap);   // [GB_CHUNK][istr], 16-byte aligned rows
+    float2 *T = reinterpret_cast<float2 *>(chunk + GB_CHUNK * P.istr); // [nsrc_cap][GB_TWP] complex row-pass output
 
     const GaborScale &sc = P.scales[s];
     const float *plane = P.planes + ((size_t)b * P.C + c) * P.H * P.Wp;
@@ -436,16 +442,14 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
         constexpr int SCOLS = (GB_TW + 2 * 96 + GB_RR + 31) / 32;        // lane columns for the widest supported row
         const int ncol = (cw + 31) / 32;                                 // <= SCOLS (h <= 96 checked on the host)
         float stage[SROWS][SCOLS];
+        // The planes are padded so that every staged address is in bounds: no per-lane guards.
         auto fetch = [&](int ch0) {
 #pragma unroll
             for (int a = 0; a < SROWS; ++a) {
-                const int r = ch0 + warp + a * GB_WARPS;
-                const float *src = plane + (size_t)min(r, P.H - 1) * P.Wp + gcol0 + lane;
+                const float *src = plane + (size_t)min(ch0 + warp + a * GB_WARPS, P.H - 1) * P.Wp + gcol0 + lane;
 #pragma unroll
-                for (int j = 0; j < SCOLS; ++j) {
-                    const int cc = lane + 32 * j;
-                    stage[a][j] = (j < ncol && r < hi && cc < cw && gcol0 + cc < P.Wp) ? __ldg(src + 32 * j) : 0.f;
-                }
+                for (int j = 0; j < SCOLS; ++j)
+                    if (j < ncol) stage[a][j] = __ldg(src + 32 * j);
             }
         };
         fetch(lo);
@@ -455,7 +459,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
             for (int a = 0; a < SROWS; ++a)
 #pragma unroll
                 for (int j = 0; j < SCOLS; ++j)
-                    if (j < ncol && lane + 32 * j < cw) chunk[(warp + a * GB_WARPS) * P.istr + lane + 32 * j] = stage[a][j];
+                    if (j < ncol) chunk[(warp + a * GB_WARPS) * P.istr + lane + 32 * j] = stage[a][j];
             __syncthreads();
             if (ch0 + GB_CHUNK < hi) fetch(ch0 + GB_CHUNK);
             const int trow = ch0 - lo + lane;
@@ -499,7 +503,7 @@ struct GaborLaunchPlan {
 
 static size_t gabor_smem_bytes(int nsrc, int hmax, int th_max)
 {
-    const int istr = (GB_TW + 2 * hmax + GB_RR) | 1;
+    const int istr = (GB_TW + 2 * hmax + GB_RR + 31) / 32 * 32 + 4;
     const int tap_slot = round_up(2 * (2 * hmax + 1 + 2 * GB_TAP_PAD + 2) + 8, 4);
     const int rowtab = round_up((th_max + GB_RC - 1) / GB_RC * GB_RC + 2 * hmax + 2 * GB_RC, 4);
     return sizeof(float) * ((size_t)2 * nsrc * GB_TWP + (size_t)GB_CHUNK * istr + 2 * (size_t)tap_slot) +
@@ -545,7 +549,7 @@ int gabor_plan(const GaborBankHost &bank, int H, int W, int C, int P, int Wp, in
     int th_max = 0;
     for (int s = 0; s < bank.S; ++s) th_max = std::max(th_max, p.TH[s]);
     p.nsrc_cap = nsrc_cap;
-    p.istr = (GB_TW + 2 * hmax + GB_RR) | 1;
+    p.istr = (GB_TW + 2 * hmax + GB_RR + 31) / 32 * 32 + 4;
     p.tap_slot = round_up(2 * (2 * hmax + 1 + 2 * GB_TAP_PAD + 2) + 8, 4);
     p.rowtab_cap = round_up((th_max + GB_RC - 1) / GB_RC * GB_RC + 2 * hmax + 2 * GB_RC, 4);
     lp.smem = gabor_smem_bytes(nsrc_cap, hmax, th_max);

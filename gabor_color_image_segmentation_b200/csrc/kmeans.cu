@@ -14,21 +14,23 @@
 // sums [B][k][D] int64; counts [B][k] int32; labels kept between iterations as one byte/pixel.
 //
 // One CTA owns one tile of 256*VEC consecutive pixels of one image.
-//   Phase A (thread = VEC pixels) streams the D planes once (128-bit loads, a rotating window of
-//   KM_PF loads in flight per thread) and keeps only the scores; the FMA chain runs as packed
-//   fma.rn.f32x2 over cluster pairs (one IEEE fp32 FMA per lane, same result as scalar FFMA),
-//   which halves the FP32 issue slots so the pass is bandwidth-bound.
+//   Phase A (thread = VEC pixels) streams the D planes exactly once through a shared-memory ring
+//   filled by the TMA engine (cp.async.bulk of one 4 KB row per plane, completion on mbarriers;
+//   VEC == 4) and keeps only the scores; the FMA chain runs as packed fma.rn.f32x2 over cluster
+//   pairs (one IEEE fp32 FMA per lane, same result as scalar FFMA), which halves the FP32 issue
+//   slots.  Alone, this phase runs at 0.96 of the measured HBM copy peak.
 //   Phase B updates the centroid sums INCREMENTALLY: because the sums are exact integers,
 //   sum_new = sum_old + q(pixels that joined) - q(pixels that left) is bit-identical to a full
 //   recomputation, and after the first iterations only a few percent of the pixels change
-//   label.  Changed pixels are compacted, re-read from L1/L2, transposed through shared memory
-//   (lane = feature) and accumulated with a warp-uniform label, so no atomics are contended.
-//     sparse path (<= 32 changed pixels in the tile): one gather, one barrier, each (cluster,
-//       feature) delta lives in exactly one lane and is published with one global atomic;
-//     dense path: 256-pixel rounds, warp-private bins, block reduction, one global atomic per
-//       (cluster, feature) per CTA.
+//   label.  Changed pixels are compacted in the CTA and their features re-read from L2/HBM.
+//     sparse path (<= 32 changed pixels in the tile): lane = feature, so each (cluster, feature)
+//       delta lives in exactly one lane and is published with one global atomic; no shared
+//       staging and no barrier;
+//     dense path: the per-cluster sums are a small exact integer GEMM on the tensor cores
+//       (mma.sync m16n8k32 s8 x u8: one-hot label differences times the byte digits of q + 2^31),
+//       128 changed pixels per round, each warp staging and consuming its own digit columns.
 //   The last CTA of an image to finish (ticket counter) turns sums into the next centroids and
-//   the next score table.
+//   the next score table; only its first warp stays for that serial tail.
 #include <type_traits>
 
 #include "common.cuh"
@@ -41,7 +43,10 @@ constexpr int KM_THREADS = 256;
 constexpr int KM_WARPS = KM_THREADS / 32;
 constexpr int KM_ROUND = 128;               // changed pixels transposed per round (dense path)
 constexpr int KM_QSTR = KM_ROUND + 1;       // odd stride of the transposed slab
-constexpr int KM_SPARSE = 32;               // sparse path handles up to this many changed pixels
+#ifndef KM_SPARSE_N
+#define KM_SPARSE_N 32
+#endif
+constexpr int KM_SPARSE = KM_SPARSE_N;               // sparse path handles up to this many changed pixels
 constexpr int KM_SSTR = KM_SPARSE + 1;
 #ifndef KM_PF_N
 #define KM_PF_N 8
@@ -404,6 +409,10 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
     const int n_chg = 0;
 #else
     const int n_chg = s_nchg;
+#endif
+#ifdef KM_SKIP_SPARSE   // timing experiment only: wrong results
+    if (n_chg <= KM_SPARSE) {
+    } else
 #endif
     if (n_chg > 0 && n_chg <= KM_SPARSE) {
         // sparse: lane = feature, so every (cluster, feature) delta lives in exactly one lane and goes

@@ -231,7 +231,8 @@ int32_t gcis_plan_create(const gcis_config *cfg, gcis_plan **out)
     p->N = H * W;
     p->D = 3 * cfg->n_scales * cfg->n_orient;
     p->P = p->bank.hmax;
-    p->Wp = round_up(W + 2 * p->P + 8, 4);
+    // wide enough that the Gabor staging never needs a column guard (gabor.cu: fetch)
+    p->Wp = round_up(round_up(W, 32) + 2 * p->P + 40, 4);
     p->Np = round_up(p->N, 32);
     int group = cfg->group;
     if (const char *e = getenv("GCIS_GROUP")) group = atoi(e);

@@ -41,20 +41,14 @@ namespace {
 
 constexpr int KM_THREADS = 256;
 constexpr int KM_WARPS = KM_THREADS / 32;
-constexpr int KM_ROUND = 128;               // changed pixels transposed per round (dense path)
-constexpr int KM_QSTR = KM_ROUND + 1;       // odd stride of the transposed slab
+constexpr int KM_ROUND = 128;               // changed pixels per tensor-core round (dense path)
 #ifndef KM_SPARSE_N
 #define KM_SPARSE_N 32
 #endif
-constexpr int KM_SPARSE = KM_SPARSE_N;               // sparse path handles up to this many changed pixels
-constexpr int KM_SSTR = KM_SPARSE + 1;
-#ifndef KM_PF_N
-#define KM_PF_N 8
-#endif
+constexpr int KM_SPARSE = KM_SPARSE_N;      // sparse path handles up to this many changed pixels
 #ifndef KM_MINB
 #define KM_MINB 4
 #endif
-constexpr int KM_PF = KM_PF_N;              // loads in flight per thread in phase A
 constexpr int KM_NONE = 255;                // "no previous label"
 
 struct KmParams {
@@ -219,7 +213,7 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
     // [ring | (aliased by the dense phase-B path) s_acc, s_q] [changed-pixel list] [s_m: m [D][K], cn [K]]
     float *s_ring = reinterpret_cast<float *>(km_smem);
     long long *s_acc = reinterpret_cast<long long *>(km_smem);                                // [warps][K][32]
-    int *s_q = reinterpret_cast<int *>(s_acc + KM_WARPS * K * 32);                            // [32][KM_QSTR]
+    int *s_q = reinterpret_cast<int *>(s_acc + KM_WARPS * K * 32);                            // digit slab [KM_BCOLS][KM_BSTR]
     constexpr size_t PHASE_B_BYTES = km_phase_b_bytes(K);
     constexpr size_t FRONT_BYTES =
         ((RING_FLOATS * sizeof(float) > PHASE_B_BYTES ? RING_FLOATS * sizeof(float) : PHASE_B_BYTES) + 15) & ~(size_t)15;

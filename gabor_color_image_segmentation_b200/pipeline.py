@@ -110,3 +110,33 @@ def dataset_scores(sums: np.ndarray) -> dict:
     reference aggregates nothing across images, script.py:22-38)."""
     n = sums[-1]
     return {k: float(sums[i] / n) for i, k in enumerate(SUM_KEYS)} | {"images": int(n)}
+
+
+def evaluate_mixed(images, ground_truths, k: int = 8, iters: int = 20, seed: int = 0, plans: Optional[dict] = None,
+                   **plan_kwargs):
+    """The reference's driver loop (script.py:22-38) over a list of images of MIXED shapes — BSDS500
+    holds both 321x481 and 481x321 images and 4..9 annotators per image.  Images are grouped by
+    shape, each group runs through one plan, and the per-image metric dicts come back in input
+    order.  `ground_truths[i]` is the list `get_segment_from_filename` returns for image i."""
+    from .groundtruth import pack_ground_truths
+    from .metrics import finish_image
+    plans = {} if plans is None else plans
+    by_shape = {}
+    for i, img in enumerate(images):
+        by_shape.setdefault(tuple(np.asarray(img).shape[:2]), []).append(i)
+    out = [None] * len(images)
+    for (H, W), idxs in by_shape.items():
+        G = max(len(ground_truths[i]) for i in idxs)
+        n_lab = max(int(np.max(g)) for i in idxs for g in ground_truths[i]) + 1
+        key = (H, W, G, k, iters)
+        if key not in plans or plans[key].n_lab_cap < n_lab or plans[key].max_batch < len(idxs):
+            plans[key] = Plan(H, W, max_batch=len(idxs), k=k, iters=iters, max_gt=G,
+                              n_lab_cap=max(64, n_lab), **plan_kwargs)
+        plan = plans[key]
+        imgs = np.stack([np.asarray(images[i], np.uint8) for i in idxs])
+        gts, n_gt = pack_ground_truths([ground_truths[i] for i in idxs], max_gt=G)
+        init = init_indices_for(idxs, H * W, k, seed)
+        c = evaluate_batch(plan, imgs, gts, init, n_gt)
+        for n, i in enumerate(idxs):
+            out[i] = finish_image(c, n)
+    return out

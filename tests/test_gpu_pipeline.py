@@ -69,3 +69,33 @@ def test_pipeline_with_pinned_tensors_and_ragged_gt():
     b = plan.pipeline_host(pin(imgs), pin(gts.view(np.int16)), pin(idx), B, n_gt)
     np.testing.assert_array_equal(a.gt_counts, b.gt_counts)
     assert (a.gt_counts[1, 1:] == 0).all() and (a.gt_counts[2, 3:] == 0).all()
+
+
+def test_mixed_shapes_and_region_scores():
+    """Landscape + portrait images with ragged annotator counts through evaluate_mixed, and the
+    region scores from the pipeline's contingency tables."""
+    from gabor_color_image_segmentation_b200 import Plan, metrics, gabor_kmeans_segment
+    from gabor_color_image_segmentation_b200.pipeline import evaluate_mixed, evaluate_batch, init_indices_for
+    from gabor_color_image_segmentation_b200.region_scores import region_scores
+    from gabor_color_image_segmentation_b200.synth import synth_image, synth_ground_truths
+    shapes = [(96, 128), (128, 96), (96, 128)]
+    imgs = [synth_image(i, h, w) for i, (h, w) in enumerate(shapes)]
+    gts = [list(synth_ground_truths(i, h, w, 2 + i)) for i, (h, w) in enumerate(shapes)]
+    res = evaluate_mixed(imgs, gts, k=5, iters=6)
+    for i, (img, gt) in enumerate(zip(imgs, gts)):
+        labels = gabor_kmeans_segment(img, n_clusters=5, n_iter=6, seed=i)
+        m = metrics(img, labels, gt)
+        m.set_metrics()
+        want = m.get_metrics()
+        for key in want:
+            assert float(res[i][key]) == float(want[key]), (i, key)
+    # region scores from the plan's device-side tables == from label_counts_host on the same labels
+    from gabor_color_image_segmentation_b200 import label_counts_host
+    H, W, G, k = 96, 128, 2, 5
+    plan = Plan(H, W, max_batch=1, k=k, iters=6, max_gt=G, n_lab_cap=64)
+    g2 = np.stack(gts[0])[None].astype(np.uint16)
+    c = evaluate_batch(plan, imgs[0][None], g2, init_indices_for([0], H * W, k), want_labels=True)
+    a = region_scores(plan.fetch_hist(1))
+    b = region_scores(label_counts_host(c.labels, g2, n_seg_cap=k, n_lab_cap=64, want_hist=True).hist)
+    for key in a:
+        assert a[key][0] == b[key][0]

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gabor_color_image_segmentation_b200 import GaborBank, Plan
 from gabor_color_image_segmentation_b200.synth import synth_batch
-B, H, W = 32, 321, 481
+B, H, W = 32, int(os.environ.get('GB_H', 321)), 481
 imgs, _ = synth_batch(4, H, W, 1)
 d_img = torch.from_numpy(np.concatenate([imgs] * 8)).cuda()
 full = GaborBank.default()
@@ -17,5 +17,5 @@ for name, bank in [("all", full)] + [("s%d" % s, GaborBank((f,), full.thetas)) f
     for _ in range(5):
         plan.gabor_features(d_img)
     e1.record(); torch.cuda.synchronize()
-    print(name, round(e0.elapsed_time(e1) / 5 / B * 1e3, 1), "us/image")
+    print(name, round(e0.elapsed_time(e1) / 5 / B * 1e3, 1), "us/image", round(e0.elapsed_time(e1) / 5 / B * 1e6 / (H * W), 3), "ns/pixel")
     plan.close()

@@ -31,6 +31,9 @@
 //       128 changed pixels per round, each warp staging and consuming its own digit columns.
 //   The last CTA of an image to finish (ticket counter) turns sums into the next centroids and
 //   the next score table; only its first warp stays for that serial tail.
+#include <cuda.h>
+
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -65,7 +68,29 @@ struct KmParams {
     int32_t *labels_out;    // [B][N], written when non-null (last iteration)
     int D, N, k, chunks, first;
     float fix_scale;
+    int pass;
 };
+
+#ifdef KM_TRACE   // timing experiment only: per-CTA phase timestamps of the first CTAs of each pass
+constexpr int KM_TR_PASSES = 20, KM_TR_CTAS = 1024, KM_TR_SLOTS = 8;
+__device__ long long km_trace_buf[KM_TR_PASSES][KM_TR_CTAS][KM_TR_SLOTS];
+__device__ __forceinline__ long long km_gtime()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define KM_TR(slot)                                                                                          \
+    do {                                                                                                     \
+        const int cta_ = blockIdx.y * gridDim.x + blockIdx.x;                                                \
+        if (threadIdx.x == 0 && cta_ < KM_TR_CTAS && P.pass < KM_TR_PASSES) {                                \
+            km_trace_buf[P.pass][cta_][slot] = clock64();                                                    \
+            if (slot == 0) km_trace_buf[P.pass][cta_][7] = km_gtime();                                       \
+        }                                                                                                    \
+    } while (0)
+#else
+#define KM_TR(slot) do { } while (0)
+#endif
 
 // Score table of one image from its centroids (all threads of the CTA; cent must be visible).
 __device__ __forceinline__ void km_write_prep(const float *cent, float *prep, int D, int k, int K, int tid, int nthr)
@@ -177,6 +202,53 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// ---- last CTA of an image: sums -> next centroids and next score table ----
+// Called by all threads after their atomics.  The barrier orders every atomic of this CTA before
+// lane 0's fence + ticket (fences are cumulative); only warp 0 stays for the ticket, so the other
+// warps never wait on its round trip.  `s_c` is k*D floats of shared scratch (the score table is
+// no longer needed: every other warp of this CTA has left).
+template <int K>
+__device__ __forceinline__ void km_ticket_finalize(const KmParams &P, int b, float *s_c)
+{
+    const int D = P.D, k = P.k;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    KM_TR(4);
+    if (warp != 0) return;
+    int last = 0;
+    if (lane == 0) {
+        __threadfence();
+        last = atomicAdd(P.done + b, 1) == P.chunks - 1;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    KM_TR(5);
+    if (!last) return;
+    __threadfence();
+    // This warp is the image's serial tail of the pass, so keep it short: independent loads are
+    // batched, and the new centroids are staged in shared memory for the table rebuild.
+    float *cent = P.cent + (size_t)b * k * D;
+    const long long *sums = P.sums + (size_t)b * k * D;
+    const int my_cnt = lane < k ? __ldcg(P.counts + b * k + lane) : 0;
+#pragma unroll 4
+    for (int i0 = 0; i0 < k * D; i0 += 32) {
+        const int i = i0 + lane;
+        const bool ok = i < k * D;
+        const int cnt = __shfl_sync(0xffffffffu, my_cnt, ok ? i / D : 0);
+        if (ok) {
+            const long long s = __ldcg(sums + i);
+            float c;
+            if (cnt > 0) c = __double2float_rn(__ddiv_rn((double)s, __dmul_rn((double)cnt, (double)P.fix_scale)));
+            else c = cent[i];
+            cent[i] = c;
+            s_c[i] = c;
+        }
+    }
+    if (lane == 0) P.done[b] = 0;
+    __syncwarp();
+    km_write_prep(s_c, P.prep + (size_t)b * (D * K + K), D, k, K, lane, 32);
+    KM_TR(6);
+}
+
 #ifndef KM_STAGES_N
 #define KM_STAGES_N 3
 #endif
@@ -230,6 +302,7 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float *feat = P.feat + (size_t)b * P.img_stride;
     const int tile0 = blockIdx.x * TILE;
+    KM_TR(0);
     float *s_cn = s_m + D * K;
 
     // Feature planes arrive through a KM_STAGES-deep shared-memory ring filled by the TMA engine
@@ -273,6 +346,7 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
     }
     if (threadIdx.x < K) s_cnt[threadIdx.x] = 0;
     __syncthreads();
+    KM_TR(1);
 
     // ---- phase A: scores and labels for VEC consecutive pixels per thread ----
     // planes are padded (VEC == 4) so a clamped vector load never leaves the plane
@@ -331,6 +405,7 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
             }
         }
     }
+    KM_TR(2);
     {
         int newl[VEC], oldl[VEC];
         bool chg[VEC];
@@ -397,6 +472,7 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
         }
     }
     __syncthreads();
+    KM_TR(3);
 
     // ---- phase B: exact fixed-point centroid deltas from the changed pixels ----
 #ifdef KM_SKIP_B   // timing experiment only: wrong results
@@ -544,43 +620,301 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
     }
     if (threadIdx.x < k && s_cnt[threadIdx.x]) atomicAdd(P.counts + b * k + threadIdx.x, s_cnt[threadIdx.x]);
 
-    // ---- last CTA of this image: sums -> next centroids and next score table ----
-    // The barrier orders every atomic of this CTA before lane 0's fence + ticket (fences are
-    // cumulative); only warp 0 stays for the ticket, so the other warps never wait on its round trip.
-    __syncthreads();
-    if (warp != 0) return;
-    int last = 0;
-    if (lane == 0) {
-        __threadfence();
-        last = atomicAdd(P.done + b, 1) == P.chunks - 1;
-    }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (!last) return;
-    __threadfence();
-    // This warp is the image's serial tail of the pass, so keep it short: independent loads are
-    // batched, and the new centroids are staged in shared memory (the score table is no longer
-    // needed: every other warp of this CTA has left) for the table rebuild.
-    float *cent = P.cent + (size_t)b * k * D;
-    const long long *sums = P.sums + (size_t)b * k * D;
-    float *s_c = s_m;
-    const int my_cnt = lane < k ? __ldcg(P.counts + b * k + lane) : 0;
-#pragma unroll 4
-    for (int i0 = 0; i0 < k * D; i0 += 32) {
-        const int i = i0 + lane;
-        const bool ok = i < k * D;
-        const int cnt = __shfl_sync(0xffffffffu, my_cnt, ok ? i / D : 0);
-        if (ok) {
-            const long long s = __ldcg(sums + i);
-            float c;
-            if (cnt > 0) c = __double2float_rn(__ddiv_rn((double)s, __dmul_rn((double)cnt, (double)P.fix_scale)));
-            else c = cent[i];
-            cent[i] = c;
-            s_c[i] = c;
+    km_ticket_finalize<K>(P, b, s_m);
+}
+
+// =================================================================================================
+// Tile-resident pass (the default when a TP-pixel tile of all D planes fits twice in an SM's shared
+// memory): one CTA owns TP consecutive pixels and pulls ALL of its D plane rows into shared memory
+// with one burst of TMA bulk copies (D x TP x 4 bytes in flight per CTA, completion on a few
+// mbarriers), scores them in arrival order (thread = pixel, same FMA chain), and then updates the
+// centroid sums straight from the resident tile, so no feature is read from L2/HBM twice in any
+// pass, including the first one where every pixel "changes".
+//   update = exact integer GEMM on the tensor cores (mma.sync m16n8k32 s8 x u8 -> s32):
+//     S[j][d] += sum_p A[j][p] * digit_b(q'[p][d]),  A[j][p] = [new_p = j] - [old_p = j],
+//     q' = rint(x * 2^shift) + 2^31 as four unsigned byte digits (offset removed with the cluster's
+//     population delta).  The B fragments are converted in registers from two 128-bit loads of a
+//     plane row (thread (g, kq) of the warp: feature 8*fg + g, pixels 4kq..4kq+3 and 16+4kq..),
+//     the four digit planes of one conversion feed four MMAs.  Rows are padded by 16 floats so that
+//     the eight rows of a fragment fall into distinct bank groups.  32-pixel blocks without any
+//     changed pixel are skipped.
+// =================================================================================================
+constexpr int KT_GROUPS = 8;   // arrival groups (one TMA box + one mbarrier each) per tile
+
+__host__ __device__ constexpr size_t kt_smem_bytes(int K, int TP, int D)
+{
+    return sizeof(float) * ((size_t)((D + KT_GROUPS - 1) / KT_GROUPS) * KT_GROUPS * TP + (size_t)((D * K + K + 3) & ~3));
+}
+
+// one TMA box: TP pixels x ppg planes of image b, landing densely as [ppg][TP]; rows or pixels
+// outside the tensor are zero-filled and still counted in the transaction bytes
+__device__ __forceinline__ void tma_box_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+template <int K, int TP>
+__global__ void __launch_bounds__(TP, 2) km_tile_kernel(const __grid_constant__ KmParams P, const __grid_constant__ CUtensorMap tmap)
+{
+    constexpr int WARPS = TP / 32, PITCH = TP;
+    constexpr int MT = (K + 15) / 16;
+    extern __shared__ __align__(128) unsigned char km_smem[];
+    const int D = P.D, N = P.N, k = P.k;
+    const int ppg = (D + KT_GROUPS - 1) / KT_GROUPS;   // planes per arrival group
+    float *s_x = reinterpret_cast<float *>(km_smem);   // [KT_GROUPS * ppg][TP]
+    float *s_m = s_x + (size_t)KT_GROUPS * ppg * PITCH;   // m [D][K], cn [K]
+    __shared__ __align__(8) unsigned long long s_bar[KT_GROUPS];
+    __shared__ __align__(16) unsigned char s_new[TP], s_old[TP];
+    __shared__ int s_cnt[K];
+    __shared__ int s_blk[WARPS];
+
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile0 = blockIdx.x * TP;
+    KM_TR(0);
+
+    if (threadIdx.x == 0) {
+        const uint32_t prep_bytes = (uint32_t)(D * K + K) * 4u, box_bytes = (uint32_t)(ppg * TP) * 4u;
+        for (int g = 0; g < KT_GROUPS; ++g) mbar_init(smem_u32(&s_bar[g]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(smem_u32(&s_bar[0]), box_bytes + prep_bytes);
+        bulk_g2s(smem_u32(s_m), P.prep + (size_t)b * (D * K + K), prep_bytes, smem_u32(&s_bar[0]));
+        tma_box_3d(smem_u32(s_x), &tmap, tile0, 0, b, smem_u32(&s_bar[0]));
+        for (int g = 1; g < KT_GROUPS && g * ppg < D; ++g) {
+            mbar_expect_tx(smem_u32(&s_bar[g]), box_bytes);
+            tma_box_3d(smem_u32(s_x + (size_t)g * ppg * PITCH), &tmap, tile0, g * ppg, b, smem_u32(&s_bar[g]));
         }
     }
-    if (lane == 0) P.done[b] = 0;
-    __syncwarp();
-    km_write_prep(s_c, P.prep + (size_t)b * (D * K + K), D, k, K, lane, 32);
+    const int p = tile0 + threadIdx.x;
+    const bool valid = p < N;
+    unsigned char *lab = P.lab8 + (size_t)b * P.lab_stride;
+    int oldl = KM_NONE;
+    if (!P.first && valid) oldl = lab[p];
+    if (threadIdx.x < K) s_cnt[threadIdx.x] = 0;
+    __syncthreads();   // barriers initialised for every waiter
+    KM_TR(1);
+
+    // ---- scores: planes in arrival order ----
+    mbar_wait(smem_u32(&s_bar[0]), 0);
+    unsigned long long s2[K / 2];
+    {
+        const float *s_cn = s_m + D * K;
+#pragma unroll
+        for (int i = 0; i < K / 2; ++i) asm("mov.b64 %0, {%1, %2};" : "=l"(s2[i]) : "f"(s_cn[2 * i]), "f"(s_cn[2 * i + 1]));
+    }
+    for (int g = 0; g < KT_GROUPS; ++g) {
+        const int d_lo = g * ppg, d_hi = min(D, d_lo + ppg);
+        if (d_lo >= d_hi) break;
+        if (g) mbar_wait(smem_u32(&s_bar[g]), 0);
+        const float *xp = s_x + (size_t)d_lo * PITCH + threadIdx.x;
+        const ulonglong2 *mrow = reinterpret_cast<const ulonglong2 *>(s_m + (size_t)d_lo * K);
+#pragma unroll 4
+        for (int d = d_lo; d < d_hi; ++d, xp += PITCH, mrow += K / 4) {
+            const float x = *xp;
+#pragma unroll
+            for (int q = 0; q < K / 4; ++q) {
+                const ulonglong2 mm = mrow[q];
+                ffma2(s2[2 * q], mm.x, x);
+                ffma2(s2[2 * q + 1], mm.y, x);
+            }
+        }
+    }
+    KM_TR(2);
+    // ---- labels, population deltas, per-block change flags ----
+    {
+        float bs, sj[2];
+        int best = 0;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(sj[0]), "=f"(sj[1]) : "l"(s2[0]));
+        bs = sj[0];
+        if (sj[1] < bs) { bs = sj[1]; best = 1; }
+#pragma unroll
+        for (int i = 1; i < K / 2; ++i) {
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(sj[0]), "=f"(sj[1]) : "l"(s2[i]));
+            if (sj[0] < bs) { bs = sj[0]; best = 2 * i; }
+            if (sj[1] < bs) { bs = sj[1]; best = 2 * i + 1; }
+        }
+        const bool chg = valid && best != oldl;
+        if (chg) lab[p] = (unsigned char)best;
+        if (valid && P.labels_out) P.labels_out[(size_t)b * N + p] = best;
+        s_new[threadIdx.x] = chg ? (unsigned char)best : (unsigned char)KM_NONE;
+        s_old[threadIdx.x] = chg ? (unsigned char)oldl : (unsigned char)KM_NONE;
+        const unsigned any = __ballot_sync(0xffffffffu, chg);
+        if (lane == 0) s_blk[warp] = any != 0;
+        if (any) {
+            int dcnt = 0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const unsigned in = __ballot_sync(0xffffffffu, chg && best == j);
+                const unsigned out = __ballot_sync(0xffffffffu, chg && oldl == j);
+                if (lane == j) dcnt = __popc(in) - __popc(out);
+            }
+            if (lane < K && dcnt) atomicAdd(&s_cnt[lane], dcnt);
+        }
+    }
+    __syncthreads();
+    KM_TR(3);
+
+    // ---- centroid-sum deltas from the resident tile (tensor cores) ----
+    unsigned blkmask = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) blkmask |= s_blk[w] ? 1u << w : 0u;
+#ifdef KM_SKIP_B   // timing experiment only: wrong results
+    blkmask = 0;
+#endif
+    if (blkmask) {
+        const int g = lane >> 2, kq = lane & 3;
+        const int n_fg = (D + 7) / 8;
+        const unsigned *newp = reinterpret_cast<const unsigned *>(s_new);
+        const unsigned *oldp = reinterpret_cast<const unsigned *>(s_old);
+        for (int fg = warp; fg < n_fg; fg += WARPS) {
+            int c[MT][4][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int dg = 0; dg < 4; ++dg)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) c[mt][dg][i] = 0;
+            const int d = fg * 8 + g;
+            const bool d_ok = d < D;
+            const float *row = s_x + (size_t)(d_ok ? d : 0) * PITCH + kq * 4;
+            for (unsigned m = blkmask; m; m &= m - 1) {
+                const int pb = __ffs(m) - 1;
+                unsigned bw[2][4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float4 x = *reinterpret_cast<const float4 *>(row + pb * 32 + h * 16);
+                    unsigned q0 = (unsigned)__float2int_rn(x.x * P.fix_scale), q1 = (unsigned)__float2int_rn(x.y * P.fix_scale);
+                    unsigned q2 = (unsigned)__float2int_rn(x.z * P.fix_scale), q3 = (unsigned)__float2int_rn(x.w * P.fix_scale);
+                    if (!d_ok) q0 = q1 = q2 = q3 = 0x80000000u;   // digit 0 after the offset
+                    const unsigned t0 = __byte_perm(q0, q1, 0x5140), t1 = __byte_perm(q2, q3, 0x5140);
+                    const unsigned t2 = __byte_perm(q0, q1, 0x7362), t3 = __byte_perm(q2, q3, 0x7362);
+                    bw[h][0] = __byte_perm(t0, t1, 0x5410);
+                    bw[h][1] = __byte_perm(t0, t1, 0x7632);
+                    bw[h][2] = __byte_perm(t2, t3, 0x5410);
+                    bw[h][3] = __byte_perm(t2, t3, 0x7632) ^ 0x80808080u;   // + 2^31
+                }
+                const unsigned n0 = newp[pb * 8 + kq], n1 = newp[pb * 8 + 4 + kq];
+                const unsigned o0 = oldp[pb * 8 + kq], o1 = oldp[pb * 8 + 4 + kq];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const unsigned r0w = (unsigned)(mt * 16 + g) * 0x01010101u, r1w = r0w + 0x08080808u;
+                    const unsigned a0 = (__vcmpeq4(n0, r0w) & 0x01010101u) | __vcmpeq4(o0, r0w);
+                    const unsigned a2 = (__vcmpeq4(n1, r0w) & 0x01010101u) | __vcmpeq4(o1, r0w);
+                    unsigned a1 = 0, a3 = 0;
+                    if (K > 8) {
+                        a1 = (__vcmpeq4(n0, r1w) & 0x01010101u) | __vcmpeq4(o0, r1w);
+                        a3 = (__vcmpeq4(n1, r1w) & 0x01010101u) | __vcmpeq4(o1, r1w);
+                    }
+#pragma unroll
+                    for (int dg = 0; dg < 4; ++dg)
+                        asm volatile(
+                            "mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                            : "+r"(c[mt][dg][0]), "+r"(c[mt][dg][1]), "+r"(c[mt][dg][2]), "+r"(c[mt][dg][3])
+                            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bw[0][dg]), "r"(bw[1][dg]));
+                }
+            }
+            // digits -> int64, remove the offset, publish: one global atomic per (cluster, feature) per CTA
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int hrow = 0; hrow < (K > 8 ? 2 : 1); ++hrow)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int j = mt * 16 + hrow * 8 + g;
+                        const int dd = fg * 8 + 2 * kq + i;
+                        long long v = (long long)c[mt][0][2 * hrow + i] + ((long long)c[mt][1][2 * hrow + i] << 8) +
+                                      ((long long)c[mt][2][2 * hrow + i] << 16) + ((long long)c[mt][3][2 * hrow + i] << 24);
+                        if (j < k && dd < D) {
+                            v -= (long long)s_cnt[j] << 31;
+                            if (v) atomicAdd(reinterpret_cast<unsigned long long *>(P.sums + ((size_t)b * k + j) * D + dd),
+                                             (unsigned long long)v);
+                        }
+                    }
+        }
+    }
+    if (threadIdx.x < k && s_cnt[threadIdx.x]) atomicAdd(P.counts + b * k + threadIdx.x, s_cnt[threadIdx.x]);
+    KM_TR(4);
+}
+
+// sums -> next centroids and next score table of every image, after a tile-resident pass
+// (same arithmetic as km_ticket_finalize; one CTA per image)
+__global__ void km_finalize_kernel(const __grid_constant__ KmParams P, int K)
+{
+    extern __shared__ __align__(128) unsigned char km_smem[];
+    float *s_c = reinterpret_cast<float *>(km_smem);   // [k][D]
+    const int b = blockIdx.x, D = P.D, k = P.k;
+    float *cent = P.cent + (size_t)b * k * D;
+    const long long *sums = P.sums + (size_t)b * k * D;
+    for (int i = threadIdx.x; i < k * D; i += blockDim.x) {
+        const int cnt = P.counts[b * k + i / D];
+        float c;
+        if (cnt > 0) c = __double2float_rn(__ddiv_rn((double)sums[i], __dmul_rn((double)cnt, (double)P.fix_scale)));
+        else c = cent[i];
+        cent[i] = c;
+        s_c[i] = c;
+    }
+    __syncthreads();
+    km_write_prep(s_c, P.prep + (size_t)b * (D * K + K), D, k, K, threadIdx.x, blockDim.x);
+}
+
+template <int K, int TP>
+int launch_tile(const KmParams &P, const CUtensorMap &tmap, int B, cudaStream_t st)
+{
+    const size_t smem = kt_smem_bytes(K, TP, P.D);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        GCIS_CUDA_TRY(cudaFuncSetAttribute(km_tile_kernel<K, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    km_tile_kernel<K, TP><<<dim3(P.chunks, B), TP, smem, st>>>(P, tmap);
+    GCIS_LAUNCH_CHECK();
+    km_finalize_kernel<<<B, 256, sizeof(float) * P.k * P.D, st>>>(P, K);
+    GCIS_LAUNCH_CHECK();
+    return GCIS_OK;
+}
+
+// feature tensor as the TMA engine sees it: (pixel, plane, image), boxes of TP pixels x ppg planes
+static int kt_make_tensor_map(CUtensorMap *map, const float *d_feat, size_t img_stride, int plane_stride, int B, int D, int tp)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        GCIS_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) return set_error(GCIS_E_CUDA, "kmeans: cuTensorMapEncodeTiled not available");
+        encode = reinterpret_cast<encode_fn>(fn);
+    }
+    const int ppg = (D + KT_GROUPS - 1) / KT_GROUPS;
+    const cuuint64_t dims[3] = {(cuuint64_t)plane_stride, (cuuint64_t)D, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)plane_stride * 4u, (cuuint64_t)img_stride * 4u};
+    const cuuint32_t box[3] = {(cuuint32_t)tp, (cuuint32_t)ppg, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(d_feat), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(GCIS_E_CUDA, "kmeans: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return GCIS_OK;
+}
+
+// tile size of the tile-resident pass: the largest of {256, 128} pixels of which two CTAs fit in one SM; 0 = none
+constexpr size_t KT_SMEM_BUDGET = 111 * 1024;
+static int kt_tile_pixels(int K, int D)
+{
+    static const int force = [] { const char *e = getenv("GCIS_KM_TP"); return e ? atoi(e) : 0; }();
+    if (force == 128 && kt_smem_bytes(K, 128, D) <= KT_SMEM_BUDGET) return 128;
+    if (kt_smem_bytes(K, 256, D) <= KT_SMEM_BUDGET) return 256;
+    if (kt_smem_bytes(K, 128, D) <= KT_SMEM_BUDGET) return 128;
+    return 0;
+}
+
+template <int K>
+int launch_tile_tp(const KmParams &P, const CUtensorMap &tmap, int B, int tp, cudaStream_t st)
+{
+    return tp == 256 ? launch_tile<K, 256>(P, tmap, B, st) : launch_tile<K, 128>(P, tmap, B, st);
 }
 
 template <int K, int VEC>
@@ -648,12 +982,23 @@ int kmeans_launch(const float *d_feat, size_t img_stride, int plane_stride, int 
     P.feat = d_feat; P.img_stride = img_stride; P.plane_stride = plane_stride;
     P.cent = cent; P.prep = prep; P.sums = sums; P.counts = counts; P.done = done;
     P.lab8 = lab8; P.lab_stride = (int)km_lab_stride(N);
-    P.D = D; P.N = N; P.k = k; P.chunks = ceil_div(N, KM_THREADS * (vec4 ? 4 : 1));
+    // tile-resident pass when a tile fits twice per SM (GCIS_KM_RING=1 forces the streaming-ring pass)
+    static const bool force_ring = [] { const char *e = getenv("GCIS_KM_RING"); return e && atoi(e) != 0; }();
+    const int tp = (vec4 && !force_ring) ? kt_tile_pixels(K, D) : 0;
+    P.D = D; P.N = N; P.k = k; P.chunks = tp ? ceil_div(N, tp) : ceil_div(N, KM_THREADS * (vec4 ? 4 : 1));
     P.fix_scale = (float)(1u << fix_shift);
+    alignas(64) CUtensorMap tmap;
+    if (tp) {
+        const int rc = kt_make_tensor_map(&tmap, d_feat, img_stride, plane_stride, B, D, tp);
+        if (rc) return rc;
+    }
     for (int t = 0; t < iters; ++t) {
         P.labels_out = (t == iters - 1) ? d_labels : nullptr;
         P.first = t == 0;
-        const int rc = vec4 ? launch_pass_k<4>(P, B, st) : launch_pass_k<1>(P, B, st);
+        P.pass = t;
+        int rc;
+        if (tp) rc = K == 8 ? launch_tile_tp<8>(P, tmap, B, tp, st) : (K == 16 ? launch_tile_tp<16>(P, tmap, B, tp, st) : launch_tile_tp<32>(P, tmap, B, tp, st));
+        else rc = vec4 ? launch_pass_k<4>(P, B, st) : launch_pass_k<1>(P, B, st);
         if (rc) return rc;
     }
     if (d_centroids)
@@ -662,3 +1007,10 @@ int kmeans_launch(const float *d_feat, size_t img_stride, int plane_stride, int 
 }
 
 }  // namespace gcis
+
+#ifdef KM_TRACE
+extern "C" __attribute__((visibility("default"))) int gcis_km_trace_read(long long *out, size_t bytes)
+{
+    return (int)cudaMemcpyFromSymbol(out, gcis::km_trace_buf, bytes);
+}
+#endif

@@ -15,6 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--images", type=int, default=2)
+    ap.add_argument("--ctas", type=int, default=0, help="CTAs to summarise (0 = one per 1024-pixel tile)")
     a = ap.parse_args()
     import torch
     from gabor_color_image_segmentation_b200 import Plan, _lib
@@ -37,7 +38,7 @@ def main():
     lib.gcis_km_trace_read.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     rc = lib.gcis_km_trace_read(buf.ctypes.data, buf.nbytes)
     assert rc == 0, rc
-    n_cta = min(C, 151 * a.images)
+    n_cta = min(C, a.ctas or 151 * a.images)
     names = ["prologue", "stream", "labels", "update", "ticket"]
     print("pass  " + "  ".join("%9s" % n for n in names) + "   cta_total   starts_spread_us")
     for p in range(P):
@@ -47,6 +48,13 @@ def main():
         tot = np.median(t[:, 5] - t[:, 0])
         g = t[:, 7]
         print("%4d  " % p + "  ".join("%9.0f" % v for v in med) + "   %9.0f   %8.2f" % (tot, (g.max() - g.min()) / 1e3))
+    if a.ctas:   # persistent tile kernel: slot 4 = end, 5 = cycles thread 0 waited for data, 6 = tiles done
+        for p in (0, 1, 5, 10, 19):
+            t = buf[p, :n_cta]
+            tot = t[:, 4] - t[:, 0]
+            print("pass %2d: kernel cycles/CTA %.0f, waiting for data %.0f (%.0f%%), tiles/CTA %.1f, cycles/tile %.0f" % (
+                p, np.median(tot), np.median(t[:, 5]), 100 * np.median(t[:, 5] / tot), np.mean(t[:, 6]), np.median(tot / t[:, 6])))
+        return
     fin = buf[:, :n_cta, 6] - buf[:, :n_cta, 5]
     print("finalize cycles (last CTA per image, pass 10):", fin[10][buf[10, :n_cta, 6] > 0])
 

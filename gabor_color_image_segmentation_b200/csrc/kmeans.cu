@@ -33,6 +33,7 @@
 //   the next score table; only its first warp stays for that serial tail.
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -636,16 +637,26 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
 //     q' = rint(x * 2^shift) + 2^31 as four unsigned byte digits (offset removed with the cluster's
 //     population delta).  The B fragments are converted in registers from two 128-bit loads of a
 //     plane row (thread (g, kq) of the warp: feature 8*fg + g, pixels 4kq..4kq+3 and 16+4kq..),
-//     the four digit planes of one conversion feed four MMAs.  32-pixel blocks without any changed
-//     pixel are skipped.
+//     the four digit planes of one conversion feed four MMAs.  Only quads (4 aligned pixels) that
+//     hold a changed pixel are listed and fed to the MMAs, eight quads per k-block.
 //   The score table m [D][K] is warp-uniform, so every plane costs each warp two 128-bit shared
 //   loads of it on top of the pixel values: V pixels per thread amortise that load-pipe cost.
 // =================================================================================================
 constexpr int KT_GROUPS = 8;   // arrival groups (one TMA box + one mbarrier each) per tile
 
+template <int K, int TP>
+struct __align__(16) KtState {
+    unsigned long long bar[KT_GROUPS];
+    unsigned char nw[TP], ol[TP];   // new / old label of changed pixels, KM_NONE otherwise
+    int cnt[K];                     // population deltas
+    unsigned char quads[TP / 4];    // quads (4 aligned pixels) with at least one changed pixel
+    int nq;
+};
+
 __host__ __device__ constexpr size_t kt_smem_bytes(int K, int TP, int D)
 {
-    return sizeof(float) * ((size_t)((D + KT_GROUPS - 1) / KT_GROUPS) * KT_GROUPS * TP + (size_t)((D * K + K + 3) & ~3));
+    const size_t state = (KT_GROUPS * 8 + 2 * TP + 4 * K + TP / 4 + 4 + 15) & ~(size_t)15;
+    return sizeof(float) * ((size_t)((D + KT_GROUPS - 1) / KT_GROUPS) * KT_GROUPS * TP + (size_t)((D * K + K + 3) & ~3)) + state;
 }
 constexpr size_t KT_SMEM_BUDGET = 111 * 1024;   // two CTAs per SM below this
 
@@ -661,16 +672,19 @@ __device__ __forceinline__ void tma_box_3d(uint32_t dst, const CUtensorMap *map,
 template <int K, int TP, int V>
 __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constant__ KmParams P, const __grid_constant__ CUtensorMap tmap)
 {
-    constexpr int THREADS = TP / V, WARPS = THREADS / 32, NBLK = TP / 32, MT = (K + 15) / 16;
+    constexpr int THREADS = TP / V, WARPS = THREADS / 32, MT = (K + 15) / 16;
     extern __shared__ __align__(128) unsigned char km_smem[];
     const int D = P.D, N = P.N, k = P.k;
     const int ppg = (D + KT_GROUPS - 1) / KT_GROUPS;   // planes per arrival group
     float *s_x = reinterpret_cast<float *>(km_smem);   // [KT_GROUPS * ppg][TP]
     float *s_m = s_x + (size_t)KT_GROUPS * ppg * TP;   // m [D][K], cn [K]
-    __shared__ __align__(8) unsigned long long s_bar[KT_GROUPS];
-    __shared__ __align__(16) unsigned char s_new[TP], s_old[TP];
-    __shared__ int s_cnt[K];
-    __shared__ int s_blk[NBLK];
+    // small state packed behind the tile (no separately rounded static segment): with D = 72, K = 8
+    // three CTAs fit in an SM's 228 KB with no room to spare
+    KtState<K, TP> &ss = *reinterpret_cast<KtState<K, TP> *>(s_m + ((D * K + K + 3) & ~3));
+    unsigned long long *s_bar = ss.bar;
+    unsigned char *s_new = ss.nw, *s_old = ss.ol, *s_quads = ss.quads;
+    int *s_cnt = ss.cnt;
+    int &s_nq = ss.nq;
 
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -697,6 +711,7 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
         else prev = lab[min(p0, P.lab_stride - 1)];
     }
     if (threadIdx.x < K) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_nq = 0;
     __syncthreads();   // barriers initialised for every waiter
     KM_TR(1);
 
@@ -776,10 +791,19 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
             else if constexpr (V == 2) *reinterpret_cast<unsigned short *>(lab + p0) = (unsigned short)packed;
             else lab[p0] = (unsigned char)packed;
         }
-        // a warp covers V blocks of 32 pixels: lanes [32 i / V, 32 (i + 1) / V) hold block V * warp + i
         const unsigned any = __ballot_sync(0xffffffffu, anyc);
-        if (lane < V) s_blk[warp * V + lane] = (any >> (lane * (32 / V))) & (V == 1 ? 0xffffffffu : ((1u << (32 / V)) - 1u)) ? 1 : 0;
         if (any) {
+            // list the quads that hold a changed pixel (4 / V lanes per quad; order is irrelevant: the sums are exact)
+            constexpr int LQ = V >= 4 ? 1 : 4 / V;
+            bool qf = anyc;
+#pragma unroll
+            for (int o = 1; o < LQ; o <<= 1) qf |= __shfl_xor_sync(0xffffffffu, qf, o) != 0;
+            const unsigned qm = __ballot_sync(0xffffffffu, qf && (lane % LQ) == 0);
+            int qbase = 0;
+            if (lane == 0) qbase = atomicAdd(&s_nq, __popc(qm));
+            qbase = __shfl_sync(0xffffffffu, qbase, 0);
+            if (qf && (lane % LQ) == 0)
+                s_quads[qbase + __popc(qm & ((1u << lane) - 1u))] = (unsigned char)((threadIdx.x * V) >> 2);
             int dcnt = 0;
 #pragma unroll
             for (int v = 0; v < V; ++v)
@@ -796,46 +820,60 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
     KM_TR(3);
 
     // ---- centroid-sum deltas from the resident tile (tensor cores) ----
-    unsigned blkmask = 0;
-#pragma unroll
-    for (int w = 0; w < NBLK; ++w) blkmask |= s_blk[w] ? 1u << w : 0u;
+    int nq = s_nq;
 #ifdef KM_SKIP_B   // timing experiment only: wrong results
-    blkmask = 0;
+    nq = 0;
 #endif
-    if (blkmask) {
+    if (nq) {
+        // A warp works on FGU feature groups (of 8 planes) at once: their load -> convert -> MMA chains are
+        // independent, which hides the chain latency when a tile has only a few changed quads.
+        constexpr int FGU = 3;
         const int g = lane >> 2, kq = lane & 3;
         const int n_fg = (D + 7) / 8;
         const unsigned *newp = reinterpret_cast<const unsigned *>(s_new);
         const unsigned *oldp = reinterpret_cast<const unsigned *>(s_old);
-        for (int fg = warp; fg < n_fg; fg += WARPS) {
-            int c[MT][4][4];
+        for (int fgb = warp; fgb < n_fg; fgb += WARPS * FGU) {
+            int c[FGU][MT][4][4];
+            const float *row[FGU];
+            bool d_ok[FGU];
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
+            for (int u = 0; u < FGU; ++u) {
 #pragma unroll
-                for (int dg = 0; dg < 4; ++dg)
+                for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) c[mt][dg][i] = 0;
-            const int d = fg * 8 + g;
-            const bool d_ok = d < D;
-            const float *row = s_x + (size_t)(d_ok ? d : 0) * TP + kq * 4;
-            for (unsigned m = blkmask; m; m &= m - 1) {
-                const int pb = __ffs(m) - 1;
-                unsigned bw[2][4];
+                    for (int dg = 0; dg < 4; ++dg)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) c[u][mt][dg][i] = 0;
+                const int d = (fgb + u * WARPS) * 8 + g;
+                d_ok[u] = d < D;
+                row[u] = s_x + (size_t)(d_ok[u] ? d : 0) * TP;
+            }
+            // eight listed quads (32 pixels) per MMA k-block: thread (g, kq) converts quads kq and 4 + kq of the block
+            for (int q0 = 0; q0 < nq; q0 += 8) {
+                int qi[2];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const float4 x = *reinterpret_cast<const float4 *>(row + pb * 32 + h * 16);
-                    unsigned q0 = (unsigned)__float2int_rn(x.x * P.fix_scale), q1 = (unsigned)__float2int_rn(x.y * P.fix_scale);
-                    unsigned q2 = (unsigned)__float2int_rn(x.z * P.fix_scale), q3 = (unsigned)__float2int_rn(x.w * P.fix_scale);
-                    if (!d_ok) q0 = q1 = q2 = q3 = 0x80000000u;   // digit 0 after the offset
-                    const unsigned t0 = __byte_perm(q0, q1, 0x5140), t1 = __byte_perm(q2, q3, 0x5140);
-                    const unsigned t2 = __byte_perm(q0, q1, 0x7362), t3 = __byte_perm(q2, q3, 0x7362);
-                    bw[h][0] = __byte_perm(t0, t1, 0x5410);
-                    bw[h][1] = __byte_perm(t0, t1, 0x7632);
-                    bw[h][2] = __byte_perm(t2, t3, 0x5410);
-                    bw[h][3] = __byte_perm(t2, t3, 0x7632) ^ 0x80808080u;   // + 2^31
+                    const int e = q0 + h * 4 + kq;
+                    qi[h] = e < nq ? (int)s_quads[e] : -1;
                 }
-                const unsigned n0 = newp[pb * 8 + kq], n1 = newp[pb * 8 + 4 + kq];
-                const unsigned o0 = oldp[pb * 8 + kq], o1 = oldp[pb * 8 + 4 + kq];
+                unsigned bw[FGU][2][4];
+#pragma unroll
+                for (int u = 0; u < FGU; ++u)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 x = *reinterpret_cast<const float4 *>(row[u] + max(qi[h], 0) * 4);
+                        unsigned w0 = (unsigned)__float2int_rn(x.x * P.fix_scale), w1 = (unsigned)__float2int_rn(x.y * P.fix_scale);
+                        unsigned w2 = (unsigned)__float2int_rn(x.z * P.fix_scale), w3 = (unsigned)__float2int_rn(x.w * P.fix_scale);
+                        if (!d_ok[u]) w0 = w1 = w2 = w3 = 0x80000000u;   // digit 0 after the offset
+                        const unsigned t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w2, w3, 0x5140);
+                        const unsigned t2 = __byte_perm(w0, w1, 0x7362), t3 = __byte_perm(w2, w3, 0x7362);
+                        bw[u][h][0] = __byte_perm(t0, t1, 0x5410);
+                        bw[u][h][1] = __byte_perm(t0, t1, 0x7632);
+                        bw[u][h][2] = __byte_perm(t2, t3, 0x5410);
+                        bw[u][h][3] = __byte_perm(t2, t3, 0x7632) ^ 0x80808080u;   // + 2^31
+                    }
+                const unsigned n0 = qi[0] >= 0 ? newp[qi[0]] : 0xffffffffu, n1 = qi[1] >= 0 ? newp[qi[1]] : 0xffffffffu;
+                const unsigned o0 = qi[0] >= 0 ? oldp[qi[0]] : 0xffffffffu, o1 = qi[1] >= 0 ? oldp[qi[1]] : 0xffffffffu;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                     const unsigned r0w = (unsigned)(mt * 16 + g) * 0x01010101u, r1w = r0w + 0x08080808u;
@@ -847,30 +885,34 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
                         a3 = (__vcmpeq4(n1, r1w) & 0x01010101u) | __vcmpeq4(o1, r1w);
                     }
 #pragma unroll
-                    for (int dg = 0; dg < 4; ++dg)
-                        asm volatile(
-                            "mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                            : "+r"(c[mt][dg][0]), "+r"(c[mt][dg][1]), "+r"(c[mt][dg][2]), "+r"(c[mt][dg][3])
-                            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bw[0][dg]), "r"(bw[1][dg]));
+                    for (int u = 0; u < FGU; ++u)
+#pragma unroll
+                        for (int dg = 0; dg < 4; ++dg)
+                            asm volatile(
+                                "mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                : "+r"(c[u][mt][dg][0]), "+r"(c[u][mt][dg][1]), "+r"(c[u][mt][dg][2]), "+r"(c[u][mt][dg][3])
+                                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bw[u][0][dg]), "r"(bw[u][1][dg]));
                 }
             }
             // digits -> int64, remove the offset, publish: one global atomic per (cluster, feature) per tile
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
+            for (int u = 0; u < FGU; ++u)
 #pragma unroll
-                for (int hrow = 0; hrow < (K > 8 ? 2 : 1); ++hrow)
+                for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int j = mt * 16 + hrow * 8 + g;
-                        const int dd = fg * 8 + 2 * kq + i;
-                        long long v = (long long)c[mt][0][2 * hrow + i] + ((long long)c[mt][1][2 * hrow + i] << 8) +
-                                      ((long long)c[mt][2][2 * hrow + i] << 16) + ((long long)c[mt][3][2 * hrow + i] << 24);
-                        if (j < k && dd < D) {
-                            v -= (long long)s_cnt[j] << 31;
-                            if (v) atomicAdd(reinterpret_cast<unsigned long long *>(P.sums + ((size_t)b * k + j) * D + dd),
-                                             (unsigned long long)v);
+                    for (int hrow = 0; hrow < (K > 8 ? 2 : 1); ++hrow)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int j = mt * 16 + hrow * 8 + g;
+                            const int dd = (fgb + u * WARPS) * 8 + 2 * kq + i;
+                            long long v = (long long)c[u][mt][0][2 * hrow + i] + ((long long)c[u][mt][1][2 * hrow + i] << 8) +
+                                          ((long long)c[u][mt][2][2 * hrow + i] << 16) + ((long long)c[u][mt][3][2 * hrow + i] << 24);
+                            if (j < k && dd < D) {
+                                v -= (long long)s_cnt[j] << 31;
+                                if (v) atomicAdd(reinterpret_cast<unsigned long long *>(P.sums + ((size_t)b * k + j) * D + dd),
+                                                 (unsigned long long)v);
+                            }
                         }
-                    }
         }
     }
     if (threadIdx.x < k && s_cnt[threadIdx.x]) atomicAdd(P.counts + b * k + threadIdx.x, s_cnt[threadIdx.x]);
@@ -901,11 +943,17 @@ __global__ void km_finalize_kernel(const __grid_constant__ KmParams P, int K)
 template <int K, int TP, int V>
 int launch_tile(const KmParams &P, const CUtensorMap &tmap, int B, cudaStream_t st)
 {
+    static_assert(sizeof(KtState<K, TP>) == ((KT_GROUPS * 8 + 2 * TP + 4 * K + TP / 4 + 4 + 15) & ~15), "kt_smem_bytes out of sync");
     const size_t smem = kt_smem_bytes(K, TP, P.D);
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         GCIS_CUDA_TRY((cudaFuncSetAttribute(km_tile_kernel<K, TP, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         attr_smem = smem;
+        if (getenv("GCIS_DEBUG")) {
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, km_tile_kernel<K, TP, V>, TP / V, smem);
+            fprintf(stderr, "[gcis] km_tile_kernel<%d,%d,%d>: %zu bytes of shared memory, %d CTAs per SM\n", K, TP, V, smem, nb);
+        }
     }
     km_tile_kernel<K, TP, V><<<dim3(P.chunks, B), TP / V, smem, st>>>(P, tmap);
     GCIS_LAUNCH_CHECK();

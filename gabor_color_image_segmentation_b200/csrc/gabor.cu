@@ -232,25 +232,30 @@ template <int R, bool CT, bool CX, class XLoad>
 __device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u64 (&P)[R], u64 (&Q)[R], float (&S)[R],
                                       const float *xvec = nullptr)
 {
-#pragma unroll 1
-    for (int m = 0; m < nblk; ++m) {
-        u64 wc[CT ? 2 * R : 1];
-        float wr[CT ? 1 : 2 * R];
+    // The window of block m is taps [base - m R, base - m R + 2R): its upper half is the lower half of
+    // block m - 1, so each block loads only its R new taps (the tap loads are warp-uniform shared loads
+    // and the load pipe, not the FMA pipe, bounds the row pass) and two register halves swap roles.
+    u64 ca[CT ? R : 1], cb[CT ? R : 1];
+    float ra[CT ? 1 : R], rb[CT ? 1 : R];
+    auto load_half = [&](int m, u64 (&c)[CT ? R : 1], float (&r)[CT ? 1 : R]) {
         if constexpr (CT) {
-            const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(w0 - (size_t)m * 2 * R);
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const ulonglong2 v = wp[q];
-                wc[2 * q] = v.x; wc[2 * q + 1] = v.y;
-            }
-        } else {
-            const float4 *wp = reinterpret_cast<const float4 *>(w0 - (size_t)m * R);
+            const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(w0 - (ptrdiff_t)m * 2 * R);
 #pragma unroll
             for (int q = 0; q < R / 2; ++q) {
+                const ulonglong2 v = wp[q];
+                c[2 * q] = v.x; c[2 * q + 1] = v.y;
+            }
+        } else {
+            const float4 *wp = reinterpret_cast<const float4 *>(w0 - (ptrdiff_t)m * R);
+#pragma unroll
+            for (int q = 0; q < R / 4; ++q) {
                 const float4 v = wp[q];
-                wr[4 * q] = v.x; wr[4 * q + 1] = v.y; wr[4 * q + 2] = v.z; wr[4 * q + 3] = v.w;
+                r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
             }
         }
+    };
+    auto block = [&](int m, const u64 (&clo)[CT ? R : 1], const u64 (&chi)[CT ? R : 1], const float (&rlo)[CT ? 1 : R],
+                     const float (&rhi)[CT ? 1 : R]) {
         float xr[R], xi[R];
         u64 xp[R];
         if (R == 4 && !CX && xvec) {   // row pass: the R inputs of a block are one aligned 128-bit load
@@ -266,14 +271,25 @@ __device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u6
             for (int i = 0; i < R; ++i) {
                 const int t = i - uu + R - 1;
                 if constexpr (CT) {
-                    fma2_vs(P[i], wc[t], xr[uu]);
-                    if constexpr (CX) fma2_vs(Q[i], wc[t], xi[uu]);
-                } else if constexpr (CX) {
-                    fma2_vs(P[i], xp[uu], wr[t]);
+                    const u64 w = t < R ? clo[t % R] : chi[t % R];
+                    fma2_vs(P[i], w, xr[uu]);
+                    if constexpr (CX) fma2_vs(Q[i], w, xi[uu]);
                 } else {
-                    S[i] = fmaf(wr[t], xr[uu], S[i]);
+                    const float w = t < R ? rlo[t % R] : rhi[t % R];
+                    if constexpr (CX) fma2_vs(P[i], xp[uu], w);
+                    else S[i] = fmaf(w, xr[uu], S[i]);
                 }
             }
+        }
+    };
+    load_half(-1, cb, rb);   // upper half of block 0
+#pragma unroll 1
+    for (int m = 0; m < nblk; m += 2) {
+        load_half(m, ca, ra);
+        block(m, ca, cb, ra, rb);
+        if (m + 1 < nblk) {
+            load_half(m + 1, cb, rb);
+            block(m + 1, cb, ca, rb, ra);
         }
     }
 }

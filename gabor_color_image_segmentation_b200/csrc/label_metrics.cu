@@ -49,25 +49,36 @@ __device__ __forceinline__ void warp_agg_inc(int32_t *base, int key)
     if (key >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(base + key, __popc(peers));
 }
 
+// The window loops below walk (row = warp + 8 i, column = lane + 32 j): no integer division by the
+// run-time window width, which dominated the instruction count of the first version of this kernel.
+constexpr int LM_WARPS = LM_THREADS / 32;
+
 // Stage a (LM_TH+2*halo) x (LM_TW+2*halo) label window; outside the image -> sentinel.
 template <typename T>
 __device__ __forceinline__ void stage_labels(const T *__restrict__ src, int H, int W, int r0, int c0, int halo,
                                              int32_t *sl, int &vmax, int &neg)
 {
     const int SW = LM_TW + 2 * halo, SH = LM_TH + 2 * halo;
-    for (int i = threadIdx.x; i < SW * SH; i += LM_THREADS) {
-        int rr = i / SW, cc = i - rr * SW;
-        int r = r0 - halo + rr, c = c0 - halo + cc;
-        int v = LM_SENTINEL;
-        if (r >= 0 && r < H && c >= 0 && c < W) {
-            v = (int)src[(size_t)r * W + c];
-            // only own pixels decide max / sign so every pixel is judged exactly once
-            if (rr >= halo && rr < halo + LM_TH && cc >= halo && cc < halo + LM_TW) {
-                vmax = max(vmax, v);
-                neg |= (v < 0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int rr = warp; rr < SH; rr += LM_WARPS) {
+        const int r = r0 - halo + rr;
+        const bool row_in = r >= 0 && r < H;
+        const bool row_own = rr >= halo && rr < halo + LM_TH;
+        const T *srow = src + (size_t)(row_in ? r : 0) * W;
+        int32_t *drow = sl + rr * SW;
+        for (int cc = lane; cc < SW; cc += 32) {
+            const int c = c0 - halo + cc;
+            int v = LM_SENTINEL;
+            if (row_in && c >= 0 && c < W) {
+                v = (int)srow[c];
+                // only own pixels decide max / sign so every pixel is judged exactly once
+                if (row_own && cc >= halo && cc < halo + LM_TW) {
+                    vmax = max(vmax, v);
+                    neg |= (v < 0);
+                }
             }
+            drow[cc] = v;
         }
-        sl[i] = v;
     }
 }
 
@@ -76,19 +87,23 @@ __device__ __forceinline__ void boundary_map(const int32_t *sl, int halo, uint8_
 {
     const int SW = LM_TW + 2 * halo;
     const int e = halo - 1, EW = LM_TW + 2 * e, EH = LM_TH + 2 * e;
-    for (int i = threadIdx.x; i < EW * EH; i += LM_THREADS) {
-        int rr = i / EW, cc = i - rr * EW;
-        const int32_t *p = sl + (rr + 1) * SW + (cc + 1);
-        int v = p[0];
-        int b = 0;
-        if (v != LM_SENTINEL) {
-            int n;
-            n = p[-SW]; b |= (n != LM_SENTINEL) & (n != v);
-            n = p[SW];  b |= (n != LM_SENTINEL) & (n != v);
-            n = p[-1];  b |= (n != LM_SENTINEL) & (n != v);
-            n = p[1];   b |= (n != LM_SENTINEL) & (n != v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int rr = warp; rr < EH; rr += LM_WARPS) {
+        const int32_t *prow = sl + (rr + 1) * SW + 1;
+        uint8_t *drow = sb + rr * EW;
+        for (int cc = lane; cc < EW; cc += 32) {
+            const int32_t *p = prow + cc;
+            const int v = p[0];
+            int b = 0;
+            if (v != LM_SENTINEL) {
+                int n;
+                n = p[-SW]; b |= (n != LM_SENTINEL) & (n != v);
+                n = p[SW];  b |= (n != LM_SENTINEL) & (n != v);
+                n = p[-1];  b |= (n != LM_SENTINEL) & (n != v);
+                n = p[1];   b |= (n != LM_SENTINEL) & (n != v);
+            }
+            drow[cc] = (uint8_t)b;
         }
-        sb[i] = (uint8_t)b;
     }
 }
 
@@ -96,21 +111,23 @@ __device__ __forceinline__ void boundary_map(const int32_t *sl, int halo, uint8_
 // pixels.  sb is the boundary map on the e-expanded window; sh is scratch.
 __device__ __forceinline__ void dilate_own(const uint8_t *sb, int halo, int lo, int hi, uint8_t *sh, uint8_t *out)
 {
+    static_assert(LM_TW == 64, "two columns per lane");
     const int e = halo - 1, EW = LM_TW + 2 * e, EH = LM_TH + 2 * e;
-    for (int i = threadIdx.x; i < EH * LM_TW; i += LM_THREADS) {
-        int rr = i / LM_TW, c = i - rr * LM_TW;
-        const uint8_t *p = sb + rr * EW + c + e;
-        int v = 0;
-        for (int d = lo; d <= hi; ++d) v |= p[d];
-        sh[i] = (uint8_t)v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int rr = warp; rr < EH; rr += LM_WARPS) {
+        const uint8_t *p = sb + rr * EW + e + lane;
+        int v0 = 0, v1 = 0;
+        for (int d = lo; d <= hi; ++d) { v0 |= p[d]; v1 |= p[d + 32]; }
+        sh[rr * LM_TW + lane] = (uint8_t)v0;
+        sh[rr * LM_TW + lane + 32] = (uint8_t)v1;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < LM_TH * LM_TW; i += LM_THREADS) {
-        int r = i / LM_TW, c = i - r * LM_TW;
-        const uint8_t *p = sh + (r + e) * LM_TW + c;
-        int v = 0;
-        for (int d = lo; d <= hi; ++d) v |= p[d * LM_TW];
-        out[i] = (uint8_t)v;
+    for (int r = warp; r < LM_TH; r += LM_WARPS) {
+        const uint8_t *p = sh + (r + e) * LM_TW + lane;
+        int v0 = 0, v1 = 0;
+        for (int d = lo; d <= hi; ++d) { v0 |= p[d * LM_TW]; v1 |= p[d * LM_TW + 32]; }
+        out[r * LM_TW + lane] = (uint8_t)v0;
+        out[r * LM_TW + lane + 32] = (uint8_t)v1;
     }
 }
 

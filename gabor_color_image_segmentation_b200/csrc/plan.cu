@@ -74,7 +74,7 @@ struct gcis_plan {
     uint16_t *d_gt = nullptr;
     int32_t *d_n_gt = nullptr, *d_init = nullptr;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_gt[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     // profiling
     bool profiling = false;
     std::vector<cudaEvent_t> events;  // 5 per group: colour | gabor | kmeans | (metrics: 2 at the end)
@@ -146,8 +146,10 @@ int segment_group(gcis_plan *p, int lane, const uint8_t *d_img, int nb, const in
 
 // Segmenter + metrics for `nb` images whose results land at image offset `off` of the plan's
 // result buffers (used by the host entry point to pipeline sub-chunks).
+// `gt_ready`, when given, is waited for just before the metrics kernels: the ground truths of a
+// host sub-chunk are uploaded behind its images, while the segmenter already runs.
 int pipeline_range(gcis_plan *p, int lane, const uint8_t *d_img, const uint16_t *d_gt, const int32_t *d_n_gt,
-                   const int32_t *d_init, int off, int nb, cudaStream_t st)
+                   const int32_t *d_init, int off, int nb, cudaStream_t st, cudaEvent_t gt_ready = nullptr)
 {
     const gcis_config &c = p->cfg;
     const size_t N = p->N, G = std::max(c.max_gt, 1);
@@ -156,6 +158,7 @@ int pipeline_range(gcis_plan *p, int lane, const uint8_t *d_img, const uint16_t 
         const int n = std::min(p->group, nb - b0);
         TRY(segment_group(p, lane, d_img + (size_t)b0 * N * 3, n, d_init + (size_t)b0 * c.k, labels + (size_t)b0 * N, nullptr, st, -1));
     }
+    if (gt_ready) GCIS_CUDA_TRY(cudaStreamWaitEvent(st, gt_ready, 0));
     return label_metrics_launch(labels, d_gt, d_n_gt, nb, c.height, c.width, c.max_gt, c.k, c.n_lab_cap, c.dil_recall,
                                 p->d_bd_count + off, p->d_gt_counts + (size_t)off * G * GCIS_GT_SLOTS,
                                 p->d_area + (size_t)off * c.k, p->d_perim + (size_t)off * c.k,
@@ -313,6 +316,7 @@ void gcis_plan_destroy(gcis_plan *p)
     for (cudaEvent_t e : p->events) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
         if (p->ev_copied[i]) cudaEventDestroy(p->ev_copied[i]);
+        if (p->ev_gt[i]) cudaEventDestroy(p->ev_gt[i]);
         if (p->ev_free[i]) cudaEventDestroy(p->ev_free[i]);
     }
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
@@ -555,6 +559,7 @@ int32_t gcis_pipeline_host(gcis_plan *p, const uint8_t *h_img, const uint16_t *h
         GCIS_CUDA_TRY(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             GCIS_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_copied[i], cudaEventDisableTiming));
+            GCIS_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_gt[i], cudaEventDisableTiming));
             GCIS_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_free[i], cudaEventDisableTiming));
         }
     }
@@ -569,15 +574,18 @@ int32_t gcis_pipeline_host(gcis_plan *p, const uint8_t *h_img, const uint16_t *h
             uint16_t *dg = p->d_gt + (size_t)buf * hc * G * N;
             int32_t *dn = p->d_n_gt + (size_t)buf * hc, *dx = p->d_init + (size_t)buf * hc * c.k;
             if (i >= 2) GCIS_CUDA_TRY(cudaStreamWaitEvent(cs, p->ev_free[buf], 0));
+            // images first: the segmenter starts as soon as they have landed; the ground truths (3.3x the
+            // bytes) follow and are only awaited by the metrics kernels
             GCIS_CUDA_TRY(cudaMemcpyAsync(di, h_img + (size_t)b0 * N * 3, (size_t)nb * N * 3, cudaMemcpyHostToDevice, cs));
+            GCIS_CUDA_TRY(cudaMemcpyAsync(dx, h_init_idx + (size_t)b0 * c.k, sizeof(int32_t) * nb * c.k, cudaMemcpyHostToDevice, cs));
+            GCIS_CUDA_TRY(cudaEventRecord(p->ev_copied[buf], cs));
             if (c.max_gt > 0)
                 GCIS_CUDA_TRY(cudaMemcpyAsync(dg, h_gt + (size_t)b0 * G * N, sizeof(uint16_t) * nb * G * N, cudaMemcpyHostToDevice, cs));
             if (h_n_gt) GCIS_CUDA_TRY(cudaMemcpyAsync(dn, h_n_gt + b0, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, cs));
-            GCIS_CUDA_TRY(cudaMemcpyAsync(dx, h_init_idx + (size_t)b0 * c.k, sizeof(int32_t) * nb * c.k, cudaMemcpyHostToDevice, cs));
-            GCIS_CUDA_TRY(cudaEventRecord(p->ev_copied[buf], cs));
+            GCIS_CUDA_TRY(cudaEventRecord(p->ev_gt[buf], cs));
             cudaStream_t ls = lanes ? p->lane_stream[buf] : st;
             GCIS_CUDA_TRY(cudaStreamWaitEvent(ls, p->ev_copied[buf], 0));
-            TRY(pipeline_range(p, lanes ? buf : 0, di, dg, h_n_gt ? dn : nullptr, dx, s0, nb, ls));
+            TRY(pipeline_range(p, lanes ? buf : 0, di, dg, h_n_gt ? dn : nullptr, dx, s0, nb, ls, p->ev_gt[buf]));
             GCIS_CUDA_TRY(cudaEventRecord(p->ev_free[buf], ls));
         }
         if (lanes)

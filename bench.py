@@ -245,13 +245,14 @@ def run_gpu(args):
         total_imgs = B * world * args.steps
         dominant = "kmeans" if stage["kmeans"] >= stage["gabor"] else "gabor"
         group = args.group or 64
-        # DRAM bytes per launch from the committed ncu capture (profiles/r01_top_kernels_ncu.md: 16-image
+        # DRAM bytes per launch from the committed ncu capture (profiles/r01_launches.csv: 16-image
         # launches, read+write, mean over the 20 passes of a group), scaled to this run's launch size
-        traffic_per_image_pass = 54.9e6
-        roof_km = {"kernel": "km_pass_kernel<8,4> (%d launches per %d-image group)" % (ITERS, group), "bound": "hbm",
+        traffic_per_image_pass = 44.7e6
+        roof_km = {"kernel": "km_tile_kernel<8,256,2> (%d launches per %d-image group, timed with their km_finalize_kernel)"
+                             % (ITERS, group), "bound": "hbm",
                    "achieved": km_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": km_gbs / hbm_peak,
                    "traffic": traffic_per_image_pass * min(group, B), "algorithmic_bytes_per_launch": (N * D * 4) * min(group, B),
-                   "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_top_kernels_ncu.md",
+                   "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_launches.csv",
                    "peak_source": peak_src, "ms_per_step": stage["kmeans"]}
         roof_gb = {"kernel": "gabor_bank_kernel", "bound": "fp32", "achieved": gb_tfs,
                    "peak": fma_peak.get("ffma_rrr_tflops"), "unit": "TFLOP/s",

@@ -88,7 +88,11 @@ def test_gabor_portrait_and_tall_images():
 
 
 @pytest.mark.parametrize("k,D,N,T", [(8, 72, 5000, 6), (3, 5, 777, 4), (16, 40, 3001, 5), (32, 72, 4096, 3),
-                                     (8, 33, 1024, 7)])
+                                     (8, 33, 1024, 7),
+                                     # tile-resident pass (N % 4 == 0): K = 16, D not a multiple of 8 or of the
+                                     # arrival groups, one tile exactly / one tile + 4 pixels, 128-pixel tiles (D = 144)
+                                     (16, 40, 3000, 5), (4, 9, 260, 6), (8, 72, 256, 4), (12, 144, 2052, 3),
+                                     (27, 30, 1284, 4)])
 def test_kmeans_bit_exact_on_random_features(k, D, N, T):
     """Teacher-forced: identical fp32 features in -> identical labels and centroids out."""
     torch = _torch()

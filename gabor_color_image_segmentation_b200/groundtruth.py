@@ -5,7 +5,7 @@ import os
 import numpy as np
 from scipy.io import loadmat
 
-__all__ = ["get_segmentation", "get_segment_from_filename", "pack_ground_truths"]
+__all__ = ["get_segmentation", "get_segment_from_filename", "pack_ground_truths", "read_seg"]
 
 
 def get_segmentation(path, filename):
@@ -50,3 +50,45 @@ def pack_ground_truths(per_image_segments, max_gt=None):
                 raise ValueError("image %d ground truth %d has shape %s, expected %s" % (b, g, s.shape, (H, W)))
             out[b, g] = s
     return out, n_gt
+
+
+def read_seg(filename, one_based=True):
+    """BSDS300 human segmentation (``data/Humans/{color,gray}/<user>/<image>.seg``, SURVEY.md section 2
+    #7: ASCII header ending in a ``data`` line, then run-length rows ``label row col_start col_end``,
+    columns inclusive) -> H x W uint16 label map.  No reference code reads these files; the decoder
+    lets the same evaluation run against BSDS300 annotations.  ``one_based`` shifts the labels to
+    1..segments, the convention of the ``.mat`` ground truths (column 0 of the contingency table empty)."""
+    width = height = None
+    with open(filename, "r") as f:
+        for line in f:
+            tok = line.split()
+            if not tok:
+                continue
+            if tok[0] == "width":
+                width = int(tok[1])
+            elif tok[0] == "height":
+                height = int(tok[1])
+            elif tok[0] == "format" and len(tok) > 1 and tok[1] != "ascii":
+                raise ValueError("%s: unsupported .seg format %r" % (filename, " ".join(tok[1:])))
+            elif tok[0] == "data":
+                break
+        if width is None or height is None:
+            raise ValueError("%s: .seg header lacks width/height" % filename)
+        runs = np.loadtxt(f, dtype=np.int64, ndmin=2)
+    if runs.size == 0 or runs.shape[1] != 4:
+        raise ValueError("%s: expected rows of 'label row col_start col_end'" % filename)
+    lab, row, c0, c1 = runs.T
+    if row.min() < 0 or row.max() >= height or c0.min() < 0 or c1.max() >= width or (c1 < c0).any() or lab.min() < 0:
+        raise ValueError("%s: run outside the %dx%d image" % (filename, height, width))
+    # expand the runs with one difference array per row: +label at col_start, -label after col_end
+    out = np.zeros((height, width + 1), np.int64)
+    covered = np.zeros((height, width + 1), np.int64)
+    v = lab + (1 if one_based else 0)
+    np.add.at(out, (row, c0), v)
+    np.add.at(out, (row, c1 + 1), -v)
+    np.add.at(covered, (row, c0), 1)
+    np.add.at(covered, (row, c1 + 1), -1)
+    covered = np.cumsum(covered, axis=1)[:, :width]
+    if (covered != 1).any():
+        raise ValueError("%s: runs overlap or leave %d pixels uncovered" % (filename, int((covered != 1).sum())))
+    return np.cumsum(out, axis=1)[:, :width].astype(np.uint16)

@@ -120,6 +120,43 @@ def test_groundtruth_loader_and_packing(tmp_path):
         pack_ground_truths([got], max_gt=2)
 
 
+def _write_seg(path, lab, zero_based=True):
+    """Run-length encode a label map the way the BSDS300 .seg files do (SURVEY.md section 2 #7)."""
+    H, W = lab.shape
+    rows = []
+    for r in range(H):
+        c = 0
+        while c < W:
+            e = c
+            while e + 1 < W and lab[r, e + 1] == lab[r, c]:
+                e += 1
+            rows.append("%d %d %d %d" % (lab[r, c], r, c, e))
+            c = e + 1
+    hdr = ["format ascii cr", "date Thu Jul 26 14:34:31 2001", "image 1", "user 1", "width %d" % W, "height %d" % H,
+           "segments %d" % (lab.max() + 1), "gray 0", "invert 0", "flipflop 0", "data"]
+    path.write_text("\n".join(hdr + rows) + "\n")
+
+
+def test_seg_reader_round_trip_and_errors(tmp_path):
+    from gabor_color_image_segmentation_b200.groundtruth import read_seg
+    from gabor_color_image_segmentation_b200.synth import synth_ground_truths
+    lab = synth_ground_truths(5, 37, 53, 1)[0].astype(np.int64) - 1      # 0-based like the .seg files
+    f = tmp_path / "a.seg"
+    _write_seg(f, lab)
+    got = read_seg(str(f))
+    assert got.dtype == np.uint16 and got.shape == lab.shape
+    np.testing.assert_array_equal(got, lab + 1)                          # .mat convention: labels 1..R
+    np.testing.assert_array_equal(read_seg(str(f), one_based=False), lab)
+    # a hole in the coverage and a run outside the image are rejected
+    txt = f.read_text().splitlines()
+    (tmp_path / "hole.seg").write_text("\n".join(txt[:-1]) + "\n")
+    with pytest.raises(ValueError):
+        read_seg(str(tmp_path / "hole.seg"))
+    (tmp_path / "oob.seg").write_text("\n".join(txt + ["0 99 0 3"]) + "\n")
+    with pytest.raises(ValueError):
+        read_seg(str(tmp_path / "oob.seg"))
+
+
 def test_synthetic_generator_is_deterministic_and_bsds_shaped():
     from gabor_color_image_segmentation_b200 import synth
     a, g = synth.synth_image(7), synth.synth_ground_truths(7)

@@ -399,6 +399,16 @@ __device__ __forceinline__ const float *stage_taps(float *dst, const float *taps
     return dst + sr + GB_TAP_PAD + 2 * h - R + 1;
 }
 
+#ifdef GB_TRACE   // timing experiment only: per-CTA cycles per phase (thread 0)
+constexpr int GB_TR_CTAS = 4096;
+__device__ long long gb_trace_buf[GB_TR_CTAS][8];
+#define GB_TR_DECL long long tr_t = clock64(), tr_acc[5] = {0, 0, 0, 0, 0}; const long long tr_t0 = tr_t
+#define GB_TR_ADD(slot) do { const long long n_ = clock64(); tr_acc[slot] += n_ - tr_t; tr_t = n_; } while (0)
+#else
+#define GB_TR_DECL do { } while (0)
+#define GB_TR_ADD(slot) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_constant__ GaborParams P)
 {
     extern __shared__ __align__(16) float smem[];
@@ -430,10 +440,12 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
     float *featb = P.feat + (size_t)b * D * P.feat_plane_stride;
     const int lane = threadIdx.x & 31;
 
+    GB_TR_DECL;
     for (int ji = 0; ji < sc.n_jobs; ++ji) {
         const GaborJob job = sc.jobs[ji];
         const int h = job.h;
         __syncthreads();  // previous job's column pass is done with T, taps and rowtab
+        GB_TR_ADD(3);     // (tail of the previous column pass)
         if (threadIdx.x == 0) { s_lo = P.H; s_hi = 0; }
         const float *w_row = stage_taps<GB_RR>(tap_row, P.taps, job.row_re, job.row_im, h);
         const float *w_col = stage_taps<GB_RC>(tap_col, P.taps, job.col_re, job.col_im, h);
@@ -478,21 +490,26 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
             }
         };
         fetch(lo);
+        GB_TR_ADD(0);
         for (int ch0 = lo; ch0 < hi; ch0 += GB_CHUNK) {
             __syncthreads();                             // chunk buffer free (and rowtab complete on 1st pass)
+            GB_TR_ADD(2);                                // (waiting for the slowest warp of the row pass)
 #pragma unroll
             for (int a = 0; a < SROWS; ++a)
 #pragma unroll
                 for (int j = 0; j < SCOLS; ++j)
                     if (j < ncol) chunk[(warp + a * GB_WARPS) * P.istr + lane + 32 * j] = stage[a][j];
             __syncthreads();
+            GB_TR_ADD(1);
             if (ch0 + GB_CHUNK < hi) fetch(ch0 + GB_CHUNK);
             const int trow = ch0 - lo + lane;
             const bool active = ch0 + lane < hi;
             if (job.row_im >= 0) row_pass_chunk<true>(chunk, P.istr, w_row, nblk_row, T, trow, active);
             else row_pass_chunk<false>(chunk, P.istr, w_row, nblk_row, T, trow, active);
+            GB_TR_ADD(2);
         }
         __syncthreads();
+        GB_TR_ADD(2);
 
         // ---- column pass: T -> |response| for theta (and pi - theta) ----
         const int d0 = (c * P.S + s) * P.O;
@@ -503,7 +520,14 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
         else if (cx) col_pass<true, false>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1);
         else if (ct) col_pass<false, true>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1);
         else col_pass<false, false>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1);
+        GB_TR_ADD(3);
     }
+#ifdef GB_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < GB_TR_CTAS) {
+        long long *o = gb_trace_buf[blockIdx.x];
+        o[0] = tr_acc[0]; o[1] = tr_acc[1]; o[2] = tr_acc[2]; o[3] = tr_acc[3]; o[4] = clock64() - tr_t0; o[5] = s;
+    }
+#endif
 }
 
 }  // namespace
@@ -624,3 +648,10 @@ int gabor_launch(GaborLaunchPlan &lp, const float *d_planes, float *d_feat, cons
 }
 
 }  // namespace gcis
+
+#ifdef GB_TRACE
+extern "C" __attribute__((visibility("default"))) int gcis_gb_trace_read(long long *out, size_t bytes)
+{
+    return (int)cudaMemcpyFromSymbol(out, gcis::gb_trace_buf, bytes);
+}
+#endif

@@ -1,4 +1,4 @@
-// kmeans.cu — Lloyd iterations as one fused assign + centroid-update kernel per iteration.
+// kmeans.cu — Lloyd iterations: one fused assign + centroid-update kernel per iteration.
 //
 // Reference: none (segmenter slot, BSD_metrics/script.py:30; spec in DESIGN.md §3.4).
 // Arithmetic contract, restated bit-for-bit by oracle/gcis_oracle.c:orc_kmeans:
@@ -13,24 +13,31 @@
 // feature plane); centroids [B][k][D]; per-image score table prep = {m [D][K], cn [K]};
 // sums [B][k][D] int64; counts [B][k] int32; labels kept between iterations as one byte/pixel.
 //
-// One CTA owns one tile of 256*VEC consecutive pixels of one image.
-//   Phase A (thread = VEC pixels) streams the D planes exactly once through a shared-memory ring
-//   filled by the TMA engine (cp.async.bulk of one 4 KB row per plane, completion on mbarriers;
-//   VEC == 4) and keeps only the scores; the FMA chain runs as packed fma.rn.f32x2 over cluster
-//   pairs (one IEEE fp32 FMA per lane, same result as scalar FFMA), which halves the FP32 issue
-//   slots.  Alone, this phase runs at 0.96 of the measured HBM copy peak.
-//   Phase B updates the centroid sums INCREMENTALLY: because the sums are exact integers,
-//   sum_new = sum_old + q(pixels that joined) - q(pixels that left) is bit-identical to a full
-//   recomputation, and after the first iterations only a few percent of the pixels change
-//   label.  Changed pixels are compacted in the CTA and their features re-read from L2/HBM.
-//     sparse path (<= 32 changed pixels in the tile): lane = feature, so each (cluster, feature)
-//       delta lives in exactly one lane and is published with one global atomic; no shared
-//       staging and no barrier;
-//     dense path: the per-cluster sums are a small exact integer GEMM on the tensor cores
-//       (mma.sync m16n8k32 s8 x u8: one-hot label differences times the byte digits of q + 2^31),
-//       128 changed pixels per round, each warp staging and consuming its own digit columns.
-//   The last CTA of an image to finish (ticket counter) turns sums into the next centroids and
-//   the next score table; only its first warp stays for that serial tail.
+// Two pass kernels share this contract (kmeans_launch picks one; both update the sums INCREMENTALLY:
+// the sums are exact integers, so sum_new = sum_old + q(pixels that joined) - q(pixels that left) is
+// bit-identical to a full recomputation, and after the first iterations few pixels change label):
+//
+//   km_tile_kernel<K,TP,V>  (default when a TP-pixel tile of all D planes fits in shared memory twice
+//     per SM and the planes are padded/aligned): the tile is pulled in with TMA tensor boxes, scored in
+//     arrival order and the label changes are folded into the sums straight from the resident tile by an
+//     exact int8 tensor-core GEMM; km_finalize_kernel turns sums into the next centroids.  See the
+//     comment block above the kernel.
+//
+//   km_pass_kernel<K,VEC>  (fallback: large D*K, or caller-supplied unpadded [D][H][W] tensors):
+//     one CTA owns 256*VEC consecutive pixels.
+//     Phase A (thread = VEC pixels) streams the D planes exactly once through a shared-memory ring
+//     filled by the TMA engine (cp.async.bulk of one 4 KB row per plane, completion on mbarriers;
+//     VEC == 4) and keeps only the scores; the FMA chain runs as packed fma.rn.f32x2 over cluster
+//     pairs (one IEEE fp32 FMA per lane, same result as scalar FFMA).
+//     Phase B compacts the changed pixels in the CTA and re-reads their features from L2/HBM:
+//       sparse path (<= 32 changed pixels in the tile): lane = feature, so each (cluster, feature)
+//         delta lives in exactly one lane and is published with one global atomic; no shared
+//         staging and no barrier;
+//       dense path: the per-cluster sums are a small exact integer GEMM on the tensor cores
+//         (mma.sync m16n8k32 s8 x u8: one-hot label differences times the byte digits of q + 2^31),
+//         128 changed pixels per round, each warp staging and consuming its own digit columns.
+//     The last CTA of an image to finish (ticket counter) turns sums into the next centroids and
+//     the next score table; only its first warp stays for that serial tail.
 #include <cuda.h>
 
 #include <cstdio>

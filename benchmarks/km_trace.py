@@ -47,7 +47,8 @@ def main():
         med = np.median(d, axis=0)
         tot = np.median(t[:, 5] - t[:, 0])
         g = t[:, 7]
-        print("%4d  " % p + "  ".join("%9.0f" % v for v in med) + "   %9.0f   %8.2f" % (tot, (g.max() - g.min()) / 1e3))
+        print("%4d  " % p + "  ".join("%9.0f" % v for v in med) + "   %9.0f   %8.2f" % (tot, (g.max() - g.min()) / 1e3)
+              + "   mean update %6.0f, tiles with update > 1000 cycles: %4.1f %%" % (d[:, 3].mean(), 100 * (d[:, 3] > 1000).mean()))
     if a.ctas:   # persistent tile kernel: slot 4 = end, 5 = cycles thread 0 waited for data, 6 = tiles done
         for p in (0, 1, 5, 10, 19):
             t = buf[p, :n_cta]

@@ -650,6 +650,7 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
 //   loads of it on top of the pixel values: V pixels per thread amortise that load-pipe cost.
 // =================================================================================================
 constexpr int KT_GROUPS = 8;   // arrival groups (one TMA box + one mbarrier each) per tile
+constexpr int KT_SPARSE = 12;  // up to this many changed pixels per tile skip the tensor-core path (K <= 8)
 
 template <int K, int TP>
 struct __align__(16) KtState {
@@ -657,12 +658,13 @@ struct __align__(16) KtState {
     unsigned char nw[TP], ol[TP];   // new / old label of changed pixels, KM_NONE otherwise
     int cnt[K];                     // population deltas
     unsigned char quads[TP / 4];    // quads (4 aligned pixels) with at least one changed pixel
-    int nq;
+    unsigned char plist[KT_SPARSE]; // the first changed pixels (sparse update)
+    int nq, npx;
 };
 
 __host__ __device__ constexpr size_t kt_smem_bytes(int K, int TP, int D)
 {
-    const size_t state = (KT_GROUPS * 8 + 2 * TP + 4 * K + TP / 4 + 4 + 15) & ~(size_t)15;
+    const size_t state = (KT_GROUPS * 8 + 2 * TP + 4 * K + TP / 4 + KT_SPARSE + 8 + 15) & ~(size_t)15;
     return sizeof(float) * ((size_t)((D + KT_GROUPS - 1) / KT_GROUPS) * KT_GROUPS * TP + (size_t)((D * K + K + 3) & ~3)) + state;
 }
 constexpr size_t KT_SMEM_BUDGET = 111 * 1024;   // two CTAs per SM below this
@@ -689,9 +691,9 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
     // three CTAs fit in an SM's 228 KB with no room to spare
     KtState<K, TP> &ss = *reinterpret_cast<KtState<K, TP> *>(s_m + ((D * K + K + 3) & ~3));
     unsigned long long *s_bar = ss.bar;
-    unsigned char *s_new = ss.nw, *s_old = ss.ol, *s_quads = ss.quads;
+    unsigned char *s_new = ss.nw, *s_old = ss.ol, *s_quads = ss.quads, *s_plist = ss.plist;
     int *s_cnt = ss.cnt;
-    int &s_nq = ss.nq;
+    int &s_nq = ss.nq, &s_npx = ss.npx;
 
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -718,7 +720,7 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
         else prev = lab[min(p0, P.lab_stride - 1)];
     }
     if (threadIdx.x < K) s_cnt[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_nq = 0;
+    if (threadIdx.x == 0) { s_nq = 0; s_npx = 0; }
     __syncthreads();   // barriers initialised for every waiter
     KM_TR(1);
 
@@ -811,6 +813,21 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
             qbase = __shfl_sync(0xffffffffu, qbase, 0);
             if (qf && (lane % LQ) == 0)
                 s_quads[qbase + __popc(qm & ((1u << lane) - 1u))] = (unsigned char)((threadIdx.x * V) >> 2);
+            if constexpr (K <= 8) {   // ... and the first KT_SPARSE changed pixels themselves
+                unsigned pm[V];
+                int pc = 0;
+#pragma unroll
+                for (int v = 0; v < V; ++v) { pm[v] = __ballot_sync(0xffffffffu, chg[v]); pc += __popc(pm[v]); }
+                int pbase = 0;
+                if (lane == 0) pbase = atomicAdd(&s_npx, pc);
+                pbase = __shfl_sync(0xffffffffu, pbase, 0);
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const int pos = pbase + __popc(pm[v] & ((1u << lane) - 1u));
+                    if (chg[v] && pos < KT_SPARSE) s_plist[pos] = (unsigned char)(threadIdx.x * V + v);
+                    pbase += __popc(pm[v]);
+                }
+            }
             int dcnt = 0;
 #pragma unroll
             for (int v = 0; v < V; ++v)
@@ -831,7 +848,29 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
 #ifdef KM_SKIP_B   // timing experiment only: wrong results
     nq = 0;
 #endif
-    if (nq) {
+    bool sparse = false;
+    if constexpr (K <= 8) sparse = nq && s_npx <= KT_SPARSE;
+    if constexpr (K <= 8) if (sparse) {
+        // A handful of changed pixels (the common case after the first passes): thread = feature, the deltas
+        // of a feature stay in registers and leave as at most K global atomics; no conversion to digits, no MMA.
+        // (All lanes of a warp read one pixel of 32 different planes: a 32-way bank conflict, on <= 12 loads.)
+        const int npx = s_npx;
+        for (int d = threadIdx.x; d < D; d += THREADS) {
+            long long acc[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) acc[j] = 0;
+            const float *xd = s_x + (size_t)d * TP;
+            for (int e = 0; e < npx; ++e) {
+                const int px = s_plist[e];
+                km_move<K>(acc, nullptr, s_new[px], s_old[px], (long long)__float2int_rn(xd[px] * P.fix_scale));
+            }
+            unsigned long long *dst = reinterpret_cast<unsigned long long *>(P.sums + (size_t)b * k * D + d);
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                if (j < k && acc[j]) atomicAdd(dst + (size_t)j * D, (unsigned long long)acc[j]);
+        }
+    }
+    if (nq && !sparse) {
         // A warp works on FGU feature groups (of 8 planes) at once: their load -> convert -> MMA chains are
         // independent, which hides the chain latency when a tile has only a few changed quads.
         constexpr int FGU = 3;
@@ -856,6 +895,7 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
                 row[u] = s_x + (size_t)(d_ok[u] ? d : 0) * TP;
             }
             // eight listed quads (32 pixels) per MMA k-block: thread (g, kq) converts quads kq and 4 + kq of the block
+#pragma unroll 2
             for (int q0 = 0; q0 < nq; q0 += 8) {
                 int qi[2];
 #pragma unroll
@@ -950,7 +990,7 @@ __global__ void km_finalize_kernel(const __grid_constant__ KmParams P, int K)
 template <int K, int TP, int V>
 int launch_tile(const KmParams &P, const CUtensorMap &tmap, int B, cudaStream_t st)
 {
-    static_assert(sizeof(KtState<K, TP>) == ((KT_GROUPS * 8 + 2 * TP + 4 * K + TP / 4 + 4 + 15) & ~15), "kt_smem_bytes out of sync");
+    static_assert(sizeof(KtState<K, TP>) == ((KT_GROUPS * 8 + 2 * TP + 4 * K + TP / 4 + KT_SPARSE + 8 + 15) & ~15), "kt_smem_bytes out of sync");
     const size_t smem = kt_smem_bytes(K, TP, P.D);
     static size_t attr_smem = 0;
     if (smem > attr_smem) {

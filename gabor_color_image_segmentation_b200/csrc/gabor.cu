@@ -183,6 +183,15 @@ constexpr int GB_WARPS = GB_THREADS / 32;
 constexpr int GB_RC = 8;         // column pass: output rows per thread
 constexpr int GB_RR = 4;         // row pass: output columns per thread (32 / 4 = 8 column blocks = 8 warps)
 constexpr int GB_CHUNK = 32;     // input rows staged per row-pass step (lane = row)
+// Narrow filters (staged row <= 64 columns, i.e. half-width <= 14): 64-row chunks, two rows per lane.  The tap
+// loads are shared by the two rows and the per-chunk staging / barrier cost is paid half as often.
+constexpr int GB_CHUNK2 = 64;
+constexpr int GB_CW2 = 64;       // staged columns per row on this path
+constexpr int GB_ISTR2 = 68;     // chunk row stride: 32 n + 4 floats
+__host__ __device__ constexpr int gb_chunk_floats(int istr)
+{
+    return GB_CHUNK * istr > GB_CHUNK2 * GB_ISTR2 ? GB_CHUNK * istr : GB_CHUNK2 * GB_ISTR2;
+}
 
 struct GaborParams {
     const float *planes;   // [B][C][H][Wp]
@@ -318,6 +327,85 @@ __device__ __forceinline__ void row_pass_chunk(const float *chunk, int istr, con
     }
 }
 
+// Row pass of a 64-row chunk: lane = image rows `lane` and `lane + 32` of the chunk, warp = block of 4 output
+// columns.  Same arithmetic per output as row_pass_chunk (one FMA per tap, taps in the same order); real taps
+// update the two rows with one packed FMA.
+template <bool CT>
+__device__ __forceinline__ void row_pass_chunk2(const float *chunk, const float *w0, int nblk, float2 *T, int trow0,
+                                                int n_rows)
+{
+    constexpr int R = 4;
+    static_assert(GB_RR == R, "two-row path is written for 4 output columns per thread");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xb = warp * R;
+    const float *s0 = chunk + lane * GB_ISTR2 + xb, *s1 = s0 + 32 * GB_ISTR2;
+    u64 P0[R], P1[R];   // CT: (Tr, Ti) of row 0 / row 1;  !CT: P0[i] = (T of row 0, T of row 1)
+#pragma unroll
+    for (int i = 0; i < R; ++i) { P0[i] = 0ull; P1[i] = 0ull; }
+    u64 ca[CT ? R : 1], cb[CT ? R : 1];
+    float ra[CT ? 1 : R], rb[CT ? 1 : R];
+    auto load_half = [&](int m, u64 (&c)[CT ? R : 1], float (&r)[CT ? 1 : R]) {
+        if constexpr (CT) {
+            const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(w0 - (ptrdiff_t)m * 2 * R);
+#pragma unroll
+            for (int q = 0; q < R / 2; ++q) {
+                const ulonglong2 v = wp[q];
+                c[2 * q] = v.x; c[2 * q + 1] = v.y;
+            }
+        } else {
+            const float4 v = *reinterpret_cast<const float4 *>(w0 - (ptrdiff_t)m * R);
+            r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+        }
+    };
+    auto block = [&](int m, const u64 (&clo)[CT ? R : 1], const u64 (&chi)[CT ? R : 1], const float (&rlo)[CT ? 1 : R],
+                     const float (&rhi)[CT ? 1 : R]) {
+        const float4 v0 = *reinterpret_cast<const float4 *>(s0 + m * 4), v1 = *reinterpret_cast<const float4 *>(s1 + m * 4);
+        const float x0[R] = {v0.x, v0.y, v0.z, v0.w}, x1[R] = {v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int uu = 0; uu < R; ++uu) {
+            u64 xp = 0ull;
+            if constexpr (!CT) asm("mov.b64 %0, {%1, %2};" : "=l"(xp) : "f"(x0[uu]), "f"(x1[uu]));
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int t = i - uu + R - 1;
+                if constexpr (CT) {
+                    const u64 w = t < R ? clo[t % R] : chi[t % R];
+                    fma2_vs(P0[i], w, x0[uu]);
+                    fma2_vs(P1[i], w, x1[uu]);
+                } else {
+                    fma2_vs(P0[i], xp, t < R ? rlo[t % R] : rhi[t % R]);
+                }
+            }
+        }
+    };
+    load_half(-1, cb, rb);
+#pragma unroll 1
+    for (int m = 0; m < nblk; m += 2) {
+        load_half(m, ca, ra);
+        block(m, ca, cb, ra, rb);
+        if (m + 1 < nblk) {
+            load_half(m + 1, cb, rb);
+            block(m + 1, cb, ca, rb, ra);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (lane + 32 * h < n_rows) {
+            float2 *dst = T + (size_t)(trow0 + lane + 32 * h) * GB_TWP + xb;
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                if constexpr (CT) {
+                    reinterpret_cast<u64 *>(dst)[i] = h ? P1[i] : P0[i];
+                } else {
+                    float a, b;
+                    unpack2(P0[i], a, b);
+                    dst[i] = make_float2(h ? b : a, 0.f);
+                }
+            }
+        }
+    }
+}
+
 // sqrt.approx (MUFU): relative error <= 2^-22, far inside the feature tolerance; the IEEE
 // sqrtf costs a Newton fix-up and a slow-path branch per output, which was 13 % of the kernel's stall samples.
 __device__ __forceinline__ float fast_sqrt(float x)
@@ -432,7 +520,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
     float *tap_col = tap_row + P.tap_slot;
     int *rowtab = reinterpret_cast<int *>(tap_col + P.tap_slot);
     float *chunk = reinterpret_cast<float *>(rowtab + P.rowtab_cap);   // [GB_CHUNK][istr], 16-byte aligned rows
-    float2 *T = reinterpret_cast<float2 *>(chunk + GB_CHUNK * P.istr); // [nsrc_cap][GB_TWP] complex row-pass output
+    float2 *T = reinterpret_cast<float2 *>(chunk + gb_chunk_floats(P.istr)); // [nsrc_cap][GB_TWP] complex row-pass output
 
     const GaborScale &sc = P.scales[s];
     const float *plane = P.planes + ((size_t)b * P.C + c) * P.H * P.Wp;
@@ -471,42 +559,72 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
         // ---- row pass: image rows [lo, hi) -> T (complex) in shared memory ----
         const int cw = GB_TW + 2 * h + GB_RR;            // staged columns per row
         const int gcol0 = x0 - h + P.P;                  // first staged column in the padded plane
-        // Staging: warp w owns chunk rows w, w+8, w+16, w+24; a lane covers columns lane + 32 j.
-        // The next chunk is fetched into registers while the current one is convolved, so the
-        // global-load latency hides behind the row pass.
         const int warp = threadIdx.x >> 5;
-        constexpr int SROWS = GB_CHUNK / GB_WARPS;                       // 4 rows per warp
-        constexpr int SCOLS = (GB_TW + 2 * 96 + GB_RR + 31) / 32;        // lane columns for the widest supported row
-        const int ncol = (cw + 31) / 32;                                 // <= SCOLS (h <= 96 checked on the host)
-        float stage[SROWS][SCOLS];
-        // The planes are padded so that every staged address is in bounds: no per-lane guards.
-        auto fetch = [&](int ch0) {
+        if (cw <= GB_CW2) {
+            // narrow filter: 64-row chunks, two rows per lane (warp w stages chunk rows w, w+8, ..., w+56)
+            constexpr int SROWS2 = GB_CHUNK2 / GB_WARPS, SCOLS2 = GB_CW2 / 32;
+            float stage2[SROWS2][SCOLS2];
+            auto fetch2 = [&](int ch0) {
 #pragma unroll
-            for (int a = 0; a < SROWS; ++a) {
-                const float *src = plane + (size_t)min(ch0 + warp + a * GB_WARPS, P.H - 1) * P.Wp + gcol0 + lane;
+                for (int a = 0; a < SROWS2; ++a) {
+                    const float *src = plane + (size_t)min(ch0 + warp + a * GB_WARPS, P.H - 1) * P.Wp + gcol0 + lane;
 #pragma unroll
-                for (int j = 0; j < SCOLS; ++j)
-                    if (j < ncol) stage[a][j] = __ldg(src + 32 * j);
+                    for (int j = 0; j < SCOLS2; ++j) stage2[a][j] = __ldg(src + 32 * j);
+                }
+            };
+            fetch2(lo);
+            GB_TR_ADD(0);
+            for (int ch0 = lo; ch0 < hi; ch0 += GB_CHUNK2) {
+                __syncthreads();                         // chunk buffer free (and rowtab complete on 1st pass)
+                GB_TR_ADD(2);
+#pragma unroll
+                for (int a = 0; a < SROWS2; ++a)
+#pragma unroll
+                    for (int j = 0; j < SCOLS2; ++j) chunk[(warp + a * GB_WARPS) * GB_ISTR2 + lane + 32 * j] = stage2[a][j];
+                __syncthreads();
+                GB_TR_ADD(1);
+                if (ch0 + GB_CHUNK2 < hi) fetch2(ch0 + GB_CHUNK2);
+                if (job.row_im >= 0) row_pass_chunk2<true>(chunk, w_row, nblk_row, T, ch0 - lo, hi - ch0);
+                else row_pass_chunk2<false>(chunk, w_row, nblk_row, T, ch0 - lo, hi - ch0);
+                GB_TR_ADD(2);
             }
-        };
-        fetch(lo);
-        GB_TR_ADD(0);
-        for (int ch0 = lo; ch0 < hi; ch0 += GB_CHUNK) {
-            __syncthreads();                             // chunk buffer free (and rowtab complete on 1st pass)
-            GB_TR_ADD(2);                                // (waiting for the slowest warp of the row pass)
-#pragma unroll
-            for (int a = 0; a < SROWS; ++a)
-#pragma unroll
-                for (int j = 0; j < SCOLS; ++j)
-                    if (j < ncol) chunk[(warp + a * GB_WARPS) * P.istr + lane + 32 * j] = stage[a][j];
-            __syncthreads();
-            GB_TR_ADD(1);
-            if (ch0 + GB_CHUNK < hi) fetch(ch0 + GB_CHUNK);
-            const int trow = ch0 - lo + lane;
-            const bool active = ch0 + lane < hi;
-            if (job.row_im >= 0) row_pass_chunk<true>(chunk, P.istr, w_row, nblk_row, T, trow, active);
-            else row_pass_chunk<false>(chunk, P.istr, w_row, nblk_row, T, trow, active);
-            GB_TR_ADD(2);
+        } else {
+            // Staging: warp w owns chunk rows w, w+8, w+16, w+24; a lane covers columns lane + 32 j.
+            // The next chunk is fetched into registers while the current one is convolved, so the
+            // global-load latency hides behind the row pass.
+            constexpr int SROWS = GB_CHUNK / GB_WARPS;                       // 4 rows per warp
+            constexpr int SCOLS = (GB_TW + 2 * 96 + GB_RR + 31) / 32;        // lane columns for the widest supported row
+            const int ncol = (cw + 31) / 32;                                 // <= SCOLS (h <= 96 checked on the host)
+            float stage[SROWS][SCOLS];
+            // The planes are padded so that every staged address is in bounds: no per-lane guards.
+            auto fetch = [&](int ch0) {
+    #pragma unroll
+                for (int a = 0; a < SROWS; ++a) {
+                    const float *src = plane + (size_t)min(ch0 + warp + a * GB_WARPS, P.H - 1) * P.Wp + gcol0 + lane;
+    #pragma unroll
+                    for (int j = 0; j < SCOLS; ++j)
+                        if (j < ncol) stage[a][j] = __ldg(src + 32 * j);
+                }
+            };
+            fetch(lo);
+            GB_TR_ADD(0);
+            for (int ch0 = lo; ch0 < hi; ch0 += GB_CHUNK) {
+                __syncthreads();                             // chunk buffer free (and rowtab complete on 1st pass)
+                GB_TR_ADD(2);                                // (waiting for the slowest warp of the row pass)
+    #pragma unroll
+                for (int a = 0; a < SROWS; ++a)
+    #pragma unroll
+                    for (int j = 0; j < SCOLS; ++j)
+                        if (j < ncol) chunk[(warp + a * GB_WARPS) * P.istr + lane + 32 * j] = stage[a][j];
+                __syncthreads();
+                GB_TR_ADD(1);
+                if (ch0 + GB_CHUNK < hi) fetch(ch0 + GB_CHUNK);
+                const int trow = ch0 - lo + lane;
+                const bool active = ch0 + lane < hi;
+                if (job.row_im >= 0) row_pass_chunk<true>(chunk, P.istr, w_row, nblk_row, T, trow, active);
+                else row_pass_chunk<false>(chunk, P.istr, w_row, nblk_row, T, trow, active);
+                GB_TR_ADD(2);
+            }
         }
         __syncthreads();
         GB_TR_ADD(2);
@@ -555,7 +673,7 @@ static size_t gabor_smem_bytes(int nsrc, int hmax, int th_max)
     const int istr = (GB_TW + 2 * hmax + GB_RR + 31) / 32 * 32 + 4;
     const int tap_slot = round_up(2 * (2 * hmax + 1 + 2 * GB_TAP_PAD + 2) + 8, 4);
     const int rowtab = round_up((th_max + GB_RC - 1) / GB_RC * GB_RC + 2 * hmax + 2 * GB_RC, 4);
-    return sizeof(float) * ((size_t)2 * nsrc * GB_TWP + (size_t)GB_CHUNK * istr + 2 * (size_t)tap_slot) +
+    return sizeof(float) * ((size_t)2 * nsrc * GB_TWP + (size_t)gb_chunk_floats(istr) + 2 * (size_t)tap_slot) +
            sizeof(int) * (size_t)rowtab;
 }
 

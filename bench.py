@@ -55,6 +55,8 @@ class ClockSampler(threading.Thread):
         self.gpu, self.samples, self.stop_flag = gpu_index, [], threading.Event()
 
     def run(self):
+        if self._run_nvml():
+            return
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
@@ -65,6 +67,30 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
+
+    def _run_nvml(self):
+        """Same fields through NVML (nvidia_ml_py): one sample every 20 ms instead of one nvidia-smi process
+        every few hundred ms, so even a 300 ms timed region is covered by a dozen samples."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            reasons_fn(h)
+        except Exception:
+            return False
+        bits = [0x8, 0x40, 0x20, 0x4]   # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        while not self.stop_flag.is_set():
+            try:
+                r = reasons_fn(h)
+                self.samples.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(max_sm),
+                                     str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)] +
+                                    ["Active" if r & b else "Not Active" for b in bits])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.02)
+        return True
 
     def summary(self):
         self.stop_flag.set()

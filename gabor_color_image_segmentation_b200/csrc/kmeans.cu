@@ -649,7 +649,8 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
 //   The score table m [D][K] is warp-uniform, so every plane costs each warp two 128-bit shared
 //   loads of it on top of the pixel values: V pixels per thread amortise that load-pipe cost.
 // =================================================================================================
-constexpr int KT_GROUPS = 8;   // arrival groups (one TMA box + one mbarrier each) per tile
+constexpr int KT_GROUPS = 3;   // arrival groups (one TMA box + one mbarrier each) per tile; measured: 1: 31.1, 2: 30.9,
+                               // 3: 30.7, 4: 31.2, 8: 32.1, 12: 34.1 ms per 200 images (each TMA issue costs the elected thread ~100 cycles)
 constexpr int KT_SPARSE = 12;  // up to this many changed pixels per tile skip the tensor-core path (K <= 8)
 
 template <int K, int TP>

@@ -651,7 +651,17 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
 // =================================================================================================
 constexpr int KT_GROUPS = 3;   // arrival groups (one TMA box + one mbarrier each) per tile; measured: 1: 31.1, 2: 30.9,
                                // 3: 30.7, 4: 31.2, 8: 32.1, 12: 34.1 ms per 200 images (each TMA issue costs the elected thread ~100 cycles)
-constexpr int KT_SPARSE = 12;  // up to this many changed pixels per tile skip the tensor-core path (K <= 8)
+#ifndef KT_SPARSE_N
+#define KT_SPARSE_N 12
+#endif
+#ifndef KT_V
+#define KT_V 2        // pixels per thread
+#endif
+#ifndef KT_UNROLL
+#define KT_UNROLL 8   // planes per unrolled step of the score loop (2: 31.1, 4: 30.8, 8: 30.4, 24: 30.5 ms per 200 images)
+#endif
+constexpr int KT_UNR = KT_UNROLL;
+constexpr int KT_SPARSE = KT_SPARSE_N;  // up to this many changed pixels per tile skip the tensor-core path (K <= 8)
 
 template <int K, int TP>
 struct __align__(16) KtState {
@@ -744,7 +754,7 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
         if (g) mbar_wait(smem_u32(&s_bar[g]), 0);
         const float *xp = s_x + (size_t)d_lo * TP + threadIdx.x * V;
         const ulonglong2 *mrow = reinterpret_cast<const ulonglong2 *>(s_m + (size_t)d_lo * K);
-#pragma unroll 4
+#pragma unroll KT_UNR
         for (int d = d_lo; d < d_hi; ++d, xp += TP, mrow += K / 4) {
             float x[V];
             if constexpr (V == 4) {
@@ -1052,7 +1062,7 @@ template <int K>
 int launch_tile_tp(const KmParams &P, const CUtensorMap &tmap, int B, int tp, cudaStream_t st)
 {
     // two pixels per thread: measured best on B200 (1: 36.9, 2: 34.4, 4: 39.0 ms per 200 images)
-    return tp == 256 ? launch_tile<K, 256, 2>(P, tmap, B, st) : launch_tile<K, 128, 2>(P, tmap, B, st);
+    return tp == 256 ? launch_tile<K, 256, KT_V>(P, tmap, B, st) : launch_tile<K, 128, (KT_V > 2 ? 2 : KT_V)>(P, tmap, B, st);
 }
 
 template <int K, int VEC>

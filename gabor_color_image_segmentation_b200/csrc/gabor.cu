@@ -237,6 +237,11 @@ __device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi)
 //  !CT &&  CX: P[i] = (A, C) += w*X
 //  !CT && !CX: S[i] = A      += w*x
 // w0 points at the window of block 0; the window moves down by R taps per block.
+#ifndef GB_SWEEP_UNROLL
+#define GB_SWEEP_UNROLL 1
+#endif
+constexpr int GB_SWEEP_UNR = GB_SWEEP_UNROLL;   // pairs of blocks per unrolled step of the sweeps
+
 template <int R, bool CT, bool CX, class XLoad>
 __device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u64 (&P)[R], u64 (&Q)[R], float (&S)[R],
                                       const float *xvec = nullptr)
@@ -292,7 +297,7 @@ __device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u6
         }
     };
     load_half(-1, cb, rb);   // upper half of block 0
-#pragma unroll 1
+#pragma unroll GB_SWEEP_UNR
     for (int m = 0; m < nblk; m += 2) {
         load_half(m, ca, ra);
         block(m, ca, cb, ra, rb);
@@ -379,7 +384,7 @@ __device__ __forceinline__ void row_pass_chunk2(const float *chunk, const float 
         }
     };
     load_half(-1, cb, rb);
-#pragma unroll 1
+#pragma unroll GB_SWEEP_UNR
     for (int m = 0; m < nblk; m += 2) {
         load_half(m, ca, ra);
         block(m, ca, cb, ra, rb);

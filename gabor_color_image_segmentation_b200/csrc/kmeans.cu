@@ -646,6 +646,8 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
 //     plane row (thread (g, kq) of the warp: feature 8*fg + g, pixels 4kq..4kq+3 and 16+4kq..),
 //     the four digit planes of one conversion feed four MMAs.  Only quads (4 aligned pixels) that
 //     hold a changed pixel are listed and fed to the MMAs, eight quads per k-block.
+//   Tiles with <= KT_SPARSE changed pixels (most tiles after the first passes; K <= 8) skip the digits
+//   and the MMAs: thread = feature keeps its deltas in registers and publishes <= k atomics.
 //   The score table m [D][K] is warp-uniform, so every plane costs each warp two 128-bit shared
 //   loads of it on top of the pixel values: V pixels per thread amortise that load-pipe cost.
 // =================================================================================================

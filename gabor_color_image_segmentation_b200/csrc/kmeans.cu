@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(KM_THREADS, K <= 8 ? KM_MINB : (K <= 16 ? 2 : 
 //   update = exact integer GEMM on the tensor cores (mma.sync m16n8k32 s8 x u8 -> s32):
 //     S[j][d] += sum_p A[j][p] * digit_b(q'[p][d]),  A[j][p] = [new_p = j] - [old_p = j],
 //     q' = rint(x * 2^shift) + 2^31 as four unsigned byte digits (offset removed with the cluster's
-//     population delta).  The B fragments are converted in registers from two 128-bit loads of a
+//     population delta, which one more MMA against a column of ones yields).  The B fragments are converted in registers from two 128-bit loads of a
 //     plane row (thread (g, kq) of the warp: feature 8*fg + g, pixels 4kq..4kq+3 and 16+4kq..),
 //     the four digit planes of one conversion feed four MMAs.  Only quads (4 aligned pixels) that
 //     hold a changed pixel are listed and fed to the MMAs, eight quads per k-block.
@@ -669,7 +669,6 @@ template <int K, int TP>
 struct __align__(16) KtState {
     unsigned long long bar[KT_GROUPS];
     unsigned char nw[TP], ol[TP];   // new / old label of changed pixels, KM_NONE otherwise
-    int cnt[K];                     // population deltas
     unsigned char quads[TP / 4];    // quads (4 aligned pixels) with at least one changed pixel
     unsigned char plist[KT_SPARSE]; // the first changed pixels (sparse update)
     int nq, npx;
@@ -677,7 +676,7 @@ struct __align__(16) KtState {
 
 __host__ __device__ constexpr size_t kt_smem_bytes(int K, int TP, int D)
 {
-    const size_t state = (KT_GROUPS * 8 + 2 * TP + 4 * K + TP / 4 + KT_SPARSE + 8 + 15) & ~(size_t)15;
+    const size_t state = (KT_GROUPS * 8 + 2 * TP + TP / 4 + KT_SPARSE + 8 + 15) & ~(size_t)15;
     return sizeof(float) * ((size_t)((D + KT_GROUPS - 1) / KT_GROUPS) * KT_GROUPS * TP + (size_t)((D * K + K + 3) & ~3)) + state;
 }
 constexpr size_t KT_SMEM_BUDGET = 111 * 1024;   // two CTAs per SM below this
@@ -705,7 +704,6 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
     KtState<K, TP> &ss = *reinterpret_cast<KtState<K, TP> *>(s_m + ((D * K + K + 3) & ~3));
     unsigned long long *s_bar = ss.bar;
     unsigned char *s_new = ss.nw, *s_old = ss.ol, *s_quads = ss.quads, *s_plist = ss.plist;
-    int *s_cnt = ss.cnt;
     int &s_nq = ss.nq, &s_npx = ss.npx;
 
     const int b = blockIdx.y;
@@ -732,7 +730,6 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
         else if constexpr (V == 2) prev = *reinterpret_cast<const unsigned short *>(lab + min(p0, P.lab_stride - 2));
         else prev = lab[min(p0, P.lab_stride - 1)];
     }
-    if (threadIdx.x < K) s_cnt[threadIdx.x] = 0;
     if (threadIdx.x == 0) { s_nq = 0; s_npx = 0; }
     __syncthreads();   // barriers initialised for every waiter
     KM_TR(1);
@@ -841,16 +838,6 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
                     pbase += __popc(pm[v]);
                 }
             }
-            int dcnt = 0;
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-#pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    const unsigned in = __ballot_sync(0xffffffffu, chg[v] && newl[v] == j);
-                    const unsigned out = __ballot_sync(0xffffffffu, chg[v] && oldl[v] == j);
-                    if (lane == j) dcnt += __popc(in) - __popc(out);
-                }
-            if (lane < K && dcnt) atomicAdd(&s_cnt[lane], dcnt);
         }
     }
     __syncthreads();
@@ -882,6 +869,15 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
             for (int j = 0; j < K; ++j)
                 if (j < k && acc[j]) atomicAdd(dst + (size_t)j * D, (unsigned long long)acc[j]);
         }
+        if (threadIdx.x >= THREADS - K) {   // population deltas: one (otherwise idle) thread per cluster
+            const int j = threadIdx.x - (THREADS - K);
+            int dcnt = 0;
+            for (int e = 0; e < npx; ++e) {
+                const int px = s_plist[e];
+                dcnt += (s_new[px] == j) - (s_old[px] == j);
+            }
+            if (j < k && dcnt) atomicAdd(P.counts + b * k + j, dcnt);
+        }
     }
     if (nq && !sparse) {
         // A warp works on FGU feature groups (of 8 planes) at once: their load -> convert -> MMA chains are
@@ -892,7 +888,11 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
         const unsigned *newp = reinterpret_cast<const unsigned *>(s_new);
         const unsigned *oldp = reinterpret_cast<const unsigned *>(s_old);
         for (int fgb = warp; fgb < n_fg; fgb += WARPS * FGU) {
-            int c[FGU][MT][4][4];
+            int c[FGU][MT][4][4], cc[MT][4];   // cc: A x ones = the clusters' population deltas (every column alike)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cc[mt][i] = 0;
             const float *row[FGU];
             bool d_ok[FGU];
 #pragma unroll
@@ -944,6 +944,10 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
                         a1 = (__vcmpeq4(n0, r1w) & 0x01010101u) | __vcmpeq4(o0, r1w);
                         a3 = (__vcmpeq4(n1, r1w) & 0x01010101u) | __vcmpeq4(o1, r1w);
                     }
+                    asm volatile(
+                        "mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                        : "+r"(cc[mt][0]), "+r"(cc[mt][1]), "+r"(cc[mt][2]), "+r"(cc[mt][3])
+                        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(0x01010101u), "r"(0x01010101u));
 #pragma unroll
                     for (int u = 0; u < FGU; ++u)
 #pragma unroll
@@ -953,6 +957,15 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
                                 : "+r"(c[u][mt][dg][0]), "+r"(c[u][mt][dg][1]), "+r"(c[u][mt][dg][2]), "+r"(c[u][mt][dg][3])
                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bw[u][0][dg]), "r"(bw[u][1][dg]));
                 }
+            }
+            if (fgb == 0 && kq == 0) {   // warp 0's first round also publishes the population deltas
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int hrow = 0; hrow < (K > 8 ? 2 : 1); ++hrow) {
+                        const int j = mt * 16 + hrow * 8 + g;
+                        if (j < k && cc[mt][2 * hrow]) atomicAdd(P.counts + b * k + j, cc[mt][2 * hrow]);
+                    }
             }
             // digits -> int64, remove the offset, publish: one global atomic per (cluster, feature) per tile
 #pragma unroll
@@ -968,14 +981,13 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
                             long long v = (long long)c[u][mt][0][2 * hrow + i] + ((long long)c[u][mt][1][2 * hrow + i] << 8) +
                                           ((long long)c[u][mt][2][2 * hrow + i] << 16) + ((long long)c[u][mt][3][2 * hrow + i] << 24);
                             if (j < k && dd < D) {
-                                v -= (long long)s_cnt[j] << 31;
+                                v -= (long long)cc[mt][2 * hrow] << 31;
                                 if (v) atomicAdd(reinterpret_cast<unsigned long long *>(P.sums + ((size_t)b * k + j) * D + dd),
                                                  (unsigned long long)v);
                             }
                         }
         }
     }
-    if (threadIdx.x < k && s_cnt[threadIdx.x]) atomicAdd(P.counts + b * k + threadIdx.x, s_cnt[threadIdx.x]);
     KM_TR(4);
 }
 
@@ -1003,7 +1015,7 @@ __global__ void km_finalize_kernel(const __grid_constant__ KmParams P, int K)
 template <int K, int TP, int V>
 int launch_tile(const KmParams &P, const CUtensorMap &tmap, int B, cudaStream_t st)
 {
-    static_assert(sizeof(KtState<K, TP>) == ((KT_GROUPS * 8 + 2 * TP + 4 * K + TP / 4 + KT_SPARSE + 8 + 15) & ~15), "kt_smem_bytes out of sync");
+    static_assert(sizeof(KtState<K, TP>) == ((KT_GROUPS * 8 + 2 * TP + TP / 4 + KT_SPARSE + 8 + 15) & ~15), "kt_smem_bytes out of sync");
     const size_t smem = kt_smem_bytes(K, TP, P.D);
     static size_t attr_smem = 0;
     if (smem > attr_smem) {

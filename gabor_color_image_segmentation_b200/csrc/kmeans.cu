@@ -944,7 +944,7 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
                         a1 = (__vcmpeq4(n0, r1w) & 0x01010101u) | __vcmpeq4(o0, r1w);
                         a3 = (__vcmpeq4(n1, r1w) & 0x01010101u) | __vcmpeq4(o1, r1w);
                     }
-                    asm volatile(
+                    asm(
                         "mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                         : "+r"(cc[mt][0]), "+r"(cc[mt][1]), "+r"(cc[mt][2]), "+r"(cc[mt][3])
                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(0x01010101u), "r"(0x01010101u));
@@ -952,7 +952,7 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
                     for (int u = 0; u < FGU; ++u)
 #pragma unroll
                         for (int dg = 0; dg < 4; ++dg)
-                            asm volatile(
+                            asm(
                                 "mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                                 : "+r"(c[u][mt][dg][0]), "+r"(c[u][mt][dg][1]), "+r"(c[u][mt][dg][2]), "+r"(c[u][mt][dg][3])
                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bw[u][0][dg]), "r"(bw[u][1][dg]));

@@ -681,6 +681,12 @@ __host__ __device__ constexpr size_t kt_smem_bytes(int K, int TP, int D)
 }
 constexpr size_t KT_SMEM_BUDGET = 111 * 1024;   // two CTAs per SM below this
 
+// Programmatic dependent launch (the pass and finalize kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization): a kernel lets its successor become resident early and
+// the successor blocks at griddep_wait() until everything before it in the stream has completed and flushed.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // one TMA box: TP pixels x ppg planes of image b, landing densely as [ppg][TP]; rows or pixels
 // outside the tensor are zero-filled and still counted in the transaction bytes
 __device__ __forceinline__ void tma_box_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
@@ -711,17 +717,21 @@ __global__ void __launch_bounds__(TP / V, 2) km_tile_kernel(const __grid_constan
     const int tile0 = blockIdx.x * TP;
     KM_TR(0);
 
+    griddep_launch_dependents();   // the finalize kernel may become resident behind the last wave of this pass
     if (threadIdx.x == 0) {
         for (int g = 0; g < KT_GROUPS; ++g) mbar_init(smem_u32(&s_bar[g]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // one TMA box of ppg planes x TP pixels per arrival group (+ the image's score table with the first)
+        // one TMA box of ppg planes x TP pixels per arrival group; the features are read-only for the whole
+        // clustering, so these loads may start before the previous pass's finalize kernel has finished
         const uint32_t prep_bytes = (uint32_t)(D * K + K) * 4u, box_bytes = (uint32_t)(ppg * TP) * 4u;
         for (int g = 0; g < KT_GROUPS && g * ppg < D; ++g) {
             mbar_expect_tx(smem_u32(&s_bar[g]), box_bytes + (g == 0 ? prep_bytes : 0u));
-            if (g == 0) bulk_g2s(smem_u32(s_m), P.prep + (size_t)b * (D * K + K), prep_bytes, smem_u32(&s_bar[0]));
             tma_box_3d(smem_u32(s_x + (size_t)g * ppg * TP), &tmap, tile0, g * ppg, b, smem_u32(&s_bar[g]));
         }
+        griddep_wait();                // score table, labels, sums and counts of the previous pass are final
+        bulk_g2s(smem_u32(s_m), P.prep + (size_t)b * (D * K + K), prep_bytes, smem_u32(&s_bar[0]));
     }
+    griddep_wait();
     const int p0 = tile0 + threadIdx.x * V;
     unsigned char *lab = P.lab8 + (size_t)b * P.lab_stride;
     unsigned prev = 0xffffffffu;   // labels of the previous iteration, in flight while the tile arrives
@@ -998,6 +1008,8 @@ __global__ void km_finalize_kernel(const __grid_constant__ KmParams P, int K)
     extern __shared__ __align__(128) unsigned char km_smem[];
     float *s_c = reinterpret_cast<float *>(km_smem);   // [k][D]
     const int b = blockIdx.x, D = P.D, k = P.k;
+    griddep_launch_dependents();   // the next pass may start loading its first tiles
+    griddep_wait();                // every atomic of the pass has landed
     float *cent = P.cent + (size_t)b * k * D;
     const long long *sums = P.sums + (size_t)b * k * D;
     for (int i = threadIdx.x; i < k * D; i += blockDim.x) {
@@ -1027,10 +1039,17 @@ int launch_tile(const KmParams &P, const CUtensorMap &tmap, int B, cudaStream_t 
             fprintf(stderr, "[gcis] km_tile_kernel<%d,%d,%d>: %zu bytes of shared memory, %d CTAs per SM\n", K, TP, V, smem, nb);
         }
     }
-    km_tile_kernel<K, TP, V><<<dim3(P.chunks, B), TP / V, smem, st>>>(P, tmap);
-    GCIS_LAUNCH_CHECK();
-    km_finalize_kernel<<<B, 256, sizeof(float) * P.k * P.D, st>>>(P, K);
-    GCIS_LAUNCH_CHECK();
+    cudaLaunchAttribute pdl;
+    pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl.val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(P.chunks, B); cfg.blockDim = dim3(TP / V); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.attrs = &pdl; cfg.numAttrs = 1;
+    GCIS_CUDA_TRY(cudaLaunchKernelEx(&cfg, km_tile_kernel<K, TP, V>, P, tmap));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cfg.gridDim = dim3(B); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = sizeof(float) * P.k * P.D;
+    GCIS_CUDA_TRY(cudaLaunchKernelEx(&cfg, km_finalize_kernel, P, K));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return GCIS_OK;
 }
 

@@ -309,23 +309,78 @@ __device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u6
 }
 
 // Row pass of one staged chunk: lane = image row, warp = block of GB_RR output columns.
+// One tap half-window (R taps) of the row pass: R complex pairs or R real taps.
+template <bool CT>
+struct RowTaps {
+    u64 c[CT ? 4 : 1];
+    float r[CT ? 1 : 4];
+    __device__ __forceinline__ void load(const float *w0, int m)
+    {
+        if constexpr (CT) {
+            const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(w0 - (ptrdiff_t)m * 8);
+            const ulonglong2 v0 = wp[0], v1 = wp[1];
+            c[0] = v0.x; c[1] = v0.y; c[2] = v1.x; c[3] = v1.y;
+        } else {
+            const float4 v = *reinterpret_cast<const float4 *>(w0 - (ptrdiff_t)m * 4);
+            r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+        }
+    }
+};
+
 template <bool CT>
 __device__ __forceinline__ void row_pass_chunk(const float *chunk, int istr, const float *w0, int nblk, float2 *T,
                                                int trow, bool active)
 {
+    // Software-pipelined form of sweep<4, CT, false>: the inputs and the new tap half of block m + 1 are
+    // loaded before the 16 FMAs of block m (three tap buffers rotate, two input buffers alternate), so the
+    // shared-memory latency of a block hides behind the previous block's math.  Per output the taps are
+    // applied in the same order as in sweep().
+    constexpr int R = 4;
+    static_assert(GB_RR == R, "row pass is written for 4 output columns per thread");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int xb = warp * GB_RR;
-    u64 Pv[GB_RR], Qv[GB_RR];
-    float Sv[GB_RR];
-#pragma unroll
-    for (int i = 0; i < GB_RR; ++i) { Pv[i] = 0ull; Qv[i] = 0ull; Sv[i] = 0.f; }
+    const int xb = warp * R;
     const float *src = chunk + lane * istr + xb;
-    sweep<GB_RR, CT, false>([&](int u, float &xr, float &xi, u64 &xp) { xr = src[u]; xi = 0.f; xp = 0ull; }, w0, nblk, Pv,
-                            Qv, Sv, GB_RR == 4 ? src : nullptr);
+    u64 Pv[R];
+    float Sv[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) { Pv[i] = 0ull; Sv[i] = 0.f; }
+    auto block = [&](const float4 &x4, const RowTaps<CT> &lo, const RowTaps<CT> &hi) {
+        const float x[R] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int uu = 0; uu < R; ++uu)
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int t = i - uu + R - 1;
+                if constexpr (CT) fma2_vs(Pv[i], t < R ? lo.c[t % R] : hi.c[t % R], x[uu]);
+                else Sv[i] = fmaf(t < R ? lo.r[t % R] : hi.r[t % R], x[uu], Sv[i]);
+            }
+    };
+    auto xload = [&](int m) { return *reinterpret_cast<const float4 *>(src + 4 * min(m, nblk - 1)); };
+    RowTaps<CT> A, B, C;
+    A.load(w0, -1);
+    B.load(w0, 0);
+    float4 x0 = xload(0), x1;
+    int m = 0;
+    // block m uses lo = taps(m), hi = taps(m - 1); the loads for block m + 1 are issued first
+#define GB_ROW_STEP(XC, XN, LO, HI, NX)            \
+    NX.load(w0, min(m + 1, nblk - 1));             \
+    XN = xload(m + 1);                             \
+    block(XC, LO, HI);                             \
+    if (++m >= nblk) break;
+#pragma unroll 1
+    for (;;) {
+        GB_ROW_STEP(x0, x1, B, A, C)
+        GB_ROW_STEP(x1, x0, C, B, A)
+        GB_ROW_STEP(x0, x1, A, C, B)
+        GB_ROW_STEP(x1, x0, B, A, C)
+        GB_ROW_STEP(x0, x1, C, B, A)
+        GB_ROW_STEP(x1, x0, A, C, B)
+    }
+#undef GB_ROW_STEP
     if (active) {
         u64 *dst = reinterpret_cast<u64 *>(T + (size_t)trow * GB_TWP + xb);
 #pragma unroll
-        for (int i = 0; i < GB_RR; ++i) {
+        for (int i = 0; i < R; ++i) {
             if constexpr (CT) dst[i] = Pv[i];                      // (Tr, Ti)
             else T[(size_t)trow * GB_TWP + xb + i] = make_float2(Sv[i], 0.f);
         }

@@ -121,6 +121,14 @@ cudaEvent_t plan_event(gcis_plan *p, size_t i)
     return p->events[i];
 }
 
+// Images per launch group for a batch of B: the batch is cut into ceil(B / capacity) groups of equal size
+// rather than full groups plus a small straggler (200 images at capacity 64: 4 x 50, not 3 x 64 + 8).
+static int balanced_group(const gcis_plan *p, int B)
+{
+    const int n = ceil_div(std::max(B, 1), p->group);
+    return ceil_div(std::max(B, 1), n);
+}
+
 // colour -> Gabor -> k-means for one group of images whose features live in plan->d_feat.
 int segment_group(gcis_plan *p, int lane, const uint8_t *d_img, int nb, const int32_t *d_init, int32_t *d_labels,
                   float *d_feat_out, cudaStream_t st, int group_index)
@@ -154,8 +162,9 @@ int pipeline_range(gcis_plan *p, int lane, const uint8_t *d_img, const uint16_t 
     const gcis_config &c = p->cfg;
     const size_t N = p->N, G = std::max(c.max_gt, 1);
     int32_t *labels = p->d_labels + (size_t)off * N;
-    for (int b0 = 0; b0 < nb; b0 += p->group) {
-        const int n = std::min(p->group, nb - b0);
+    const int grp = balanced_group(p, nb);
+    for (int b0 = 0; b0 < nb; b0 += grp) {
+        const int n = std::min(grp, nb - b0);
         TRY(segment_group(p, lane, d_img + (size_t)b0 * N * 3, n, d_init + (size_t)b0 * c.k, labels + (size_t)b0 * N, nullptr, st, -1));
     }
     if (gt_ready) GCIS_CUDA_TRY(cudaStreamWaitEvent(st, gt_ready, 0));
@@ -382,8 +391,9 @@ int32_t gcis_segment_device(gcis_plan *p, const uint8_t *d_img, int32_t B, const
         for (int l = 0; l < 2; ++l) GCIS_CUDA_TRY(cudaStreamWaitEvent(p->lane_stream[l], p->ev_fork, 0));
     }
     int gi = 0;
-    for (int b0 = 0; b0 < B; b0 += p->group, ++gi) {
-        const int nb = std::min(p->group, B - b0);
+    const int grp = balanced_group(p, B);
+    for (int b0 = 0; b0 < B; b0 += grp, ++gi) {
+        const int nb = std::min(grp, B - b0);
         const int lane = lanes ? (gi & 1) : 0;
         TRY(segment_group(p, lane, d_img + b0 * img_stride, nb, d_init_idx + (size_t)b0 * p->cfg.k,
                           d_labels + (size_t)b0 * p->N, nullptr, lanes ? p->lane_stream[lane] : st, gi));
@@ -568,8 +578,9 @@ int32_t gcis_pipeline_host(gcis_plan *p, const uint8_t *h_img, const uint16_t *h
     for (int m0 = 0; m0 < B; m0 += c.max_batch) {          // the result buffers hold max_batch images
         const int mb = std::min<int>(c.max_batch, B - m0);
         int i = 0;
-        for (int s0 = 0; s0 < mb; s0 += (int)hc, ++i) {
-            const int nb = std::min<int>((int)hc, mb - s0), buf = i & 1, b0 = m0 + s0;
+        const int sub = balanced_group(p, mb);               // equal sub-chunks, each at most hc images
+        for (int s0 = 0; s0 < mb; s0 += sub, ++i) {
+            const int nb = std::min<int>(sub, mb - s0), buf = i & 1, b0 = m0 + s0;
             uint8_t *di = p->d_img + (size_t)buf * hc * N * 3;
             uint16_t *dg = p->d_gt + (size_t)buf * hc * G * N;
             int32_t *dn = p->d_n_gt + (size_t)buf * hc, *dx = p->d_init + (size_t)buf * hc * c.k;

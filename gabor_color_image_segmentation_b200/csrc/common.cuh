@@ -43,6 +43,19 @@ __host__ __device__ __forceinline__ int reflect_index(int i, int n)
     return i < n ? i : p - 1 - i;
 }
 
+// Largest dynamic shared-memory size already enabled for one kernel, per device ordinal
+// (cudaFuncSetAttribute is a per-device setting; the host side drives one device per process,
+// but a process that switches devices must not inherit another device's state).
+struct SmemAttrCache {
+    size_t v[64] = {};
+    size_t &cur()
+    {
+        int d = 0;
+        cudaGetDevice(&d);
+        return v[d & 63];
+    }
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 

@@ -815,7 +815,8 @@ int gabor_launch(GaborLaunchPlan &lp, const float *d_planes, float *d_feat, cons
     }
     p.first_block[p.S] = acc;
     lp.blocks = acc;
-    static size_t attr_smem = 0;
+    static SmemAttrCache attr_cache;
+    size_t &attr_smem = attr_cache.cur();
     if (lp.smem > attr_smem) {
         GCIS_CUDA_TRY(cudaFuncSetAttribute(gabor_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
         attr_smem = lp.smem;

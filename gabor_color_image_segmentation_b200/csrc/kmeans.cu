@@ -1029,7 +1029,8 @@ int launch_tile(const KmParams &P, const CUtensorMap &tmap, int B, cudaStream_t 
 {
     static_assert(sizeof(KtState<K, TP>) == ((KT_GROUPS * 8 + 2 * TP + TP / 4 + KT_SPARSE + 8 + 15) & ~15), "kt_smem_bytes out of sync");
     const size_t smem = kt_smem_bytes(K, TP, P.D);
-    static size_t attr_smem = 0;
+    static SmemAttrCache attr_cache;
+    size_t &attr_smem = attr_cache.cur();
     if (smem > attr_smem) {
         GCIS_CUDA_TRY((cudaFuncSetAttribute(km_tile_kernel<K, TP, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         attr_smem = smem;
@@ -1103,7 +1104,8 @@ int launch_pass(const KmParams &P, int B, cudaStream_t st)
 {
     const size_t smem = km_smem_bytes(K, VEC, P.D);
     if (smem > 200 * 1024) return set_error(GCIS_E_INVALID, "kmeans: D=%d too large for shared memory", P.D);
-    static size_t attr_smem = 0;
+    static SmemAttrCache attr_cache;
+    size_t &attr_smem = attr_cache.cur();
     if (smem > attr_smem) {
         GCIS_CUDA_TRY(cudaFuncSetAttribute(km_pass_kernel<K, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;

@@ -334,7 +334,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=200, help="images per step per GPU")
     ap.add_argument("--unique", type=int, default=48, help="distinct synthetic images generated per rank (cycled)")
-    ap.add_argument("--group", type=int, default=0, help="images per L2-resident group (0 = library default)")
+    ap.add_argument("--group", type=int, default=0, help="images per launch group (0 = library default, 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -122,10 +122,20 @@ class Plan:
                    "gcis_gabor_features")
         return feat
 
+    def _chk_init(self, init_idx, B):
+        if tuple(init_idx.shape) != (B, self.k):
+            raise ValueError(f"init_idx must be [{B},{self.k}] (one pixel index per cluster), got {tuple(init_idx.shape)}")
+
     def kmeans(self, feat, init_idx):
         torch = _torch()
+        if (not isinstance(feat, torch.Tensor) or not feat.is_cuda or feat.dtype != torch.float32 or feat.dim() != 4
+                or tuple(feat.shape[1:]) != (self.D, self.H, self.W)):
+            raise ValueError(f"feat must be a CUDA float32 tensor [B,{self.D},{self.H},{self.W}]")
+        if not 1 <= feat.shape[0] <= self.max_batch:
+            raise ValueError(f"feat holds {feat.shape[0]} images, plan capacity is {self.max_batch}")
         feat = feat.contiguous()
         B = feat.shape[0]
+        self._chk_init(init_idx, B)
         idx = init_idx.to(device=feat.device, dtype=torch.int32).contiguous()
         labels = torch.empty((B, self.H, self.W), dtype=torch.int32, device=feat.device)
         cent = torch.empty((B, self.k, self.D), dtype=torch.float32, device=feat.device)
@@ -137,6 +147,7 @@ class Plan:
         torch = _torch()
         img = self._chk_img(img)
         B = img.shape[0]
+        self._chk_init(init_idx, B)
         idx = init_idx.to(device=img.device, dtype=torch.int32).contiguous()
         labels = torch.empty((B, self.H, self.W), dtype=torch.int32, device=img.device)
         _lib.check(self.lib.gcis_segment_device(self._h, img.data_ptr(), B, idx.data_ptr(), labels.data_ptr(),
@@ -154,6 +165,9 @@ class Plan:
         if tuple(gt.shape) != (B, self.max_gt, self.H, self.W):
             raise ValueError(f"gt must be [B,{self.max_gt},{self.H},{self.W}]")
         gt = gt.contiguous()
+        self._chk_init(init_idx, B)
+        if n_gt is not None and tuple(n_gt.shape) != (B,):
+            raise ValueError(f"n_gt must be [{B}]")
         idx = init_idx.to(device=img.device, dtype=torch.int32).contiguous()
         ng = n_gt.to(device=img.device, dtype=torch.int32).contiguous() if n_gt is not None else None
         _lib.check(self.lib.gcis_pipeline_device(self._h, img.data_ptr(), gt.data_ptr(),
@@ -174,6 +188,10 @@ class Plan:
         st = o["status"]
         if st.any():
             bad = int(np.flatnonzero(st)[0])
+            if int(st[bad]) & _lib.ST_LAB_OVER:
+                raise _lib.GcisError(f"image {bad}: a ground truth has max(gt)+1 = {int(o['n_lab'][bad].max())} regions, "
+                                     f"above the plan's n_lab_cap = {self.n_lab_cap}; build the plan with a larger "
+                                     "n_lab_cap (pipeline.evaluate_batch / evaluate_mixed size it from the data)")
             raise _lib.GcisError(f"image {bad}: label out of range (status {int(st[bad])})")
         ng = np.full(B, self.max_gt, np.int32) if n_gt is None else np.asarray(n_gt, np.int32)
         n_seg = np.zeros(B, np.int32)
@@ -206,9 +224,29 @@ class Plan:
         numpy arrays or (pinned) CPU torch tensors of the documented shapes."""
         def addr(x):
             return x.ctypes.data if isinstance(x, np.ndarray) else x.data_ptr()
+
+        def chk(x, name, shape, itemsize):
+            # the C ABI reads shape-many elements from a raw address: a wrong shape or dtype would be an
+            # out-of-bounds read inside libgcis.so, so it is rejected here
+            if isinstance(x, np.ndarray):
+                ok = x.flags["C_CONTIGUOUS"] and x.dtype.itemsize == itemsize and x.dtype.kind in "iu"
+            else:
+                ok = (not x.is_cuda) and x.is_contiguous() and x.element_size() == itemsize and not x.dtype.is_floating_point
+            if not ok or tuple(x.shape) != shape:
+                raise ValueError(f"{name} must be a contiguous host array of shape {shape} with {itemsize}-byte integers, "
+                                 f"got shape {tuple(x.shape)} dtype {x.dtype}")
+        B = int(B)
+        if B < 1:
+            raise ValueError("B must be >= 1")
+        chk(img_ptr, "imgs", (B, self.H, self.W, 3), 1)
+        if self.max_gt > 0:
+            chk(gt_ptr, "gts", (B, self.max_gt, self.H, self.W), 2)
+        chk(init_ptr, "init_idx", (B, self.k), 4)
         o = self._alloc_out(B, want_labels)
         ng = None if n_gt is None else np.ascontiguousarray(n_gt, np.int32)
-        _lib.check(self.lib.gcis_pipeline_host(self._h, addr(img_ptr), addr(gt_ptr),
+        if ng is not None and (ng.shape != (B,) or ng.min() < 0 or ng.max() > self.max_gt):
+            raise ValueError(f"n_gt must be [{B}] with values in 0..{self.max_gt}")
+        _lib.check(self.lib.gcis_pipeline_host(self._h, addr(img_ptr), addr(gt_ptr) if self.max_gt > 0 else None,
                                                ng.ctypes.data if ng is not None else None, addr(init_ptr), B,
                                                o["bd"].ctypes.data, o["gc"].ctypes.data, o["area"].ctypes.data,
                                                o["perim"].ctypes.data, o["n_lab"].ctypes.data,

@@ -48,6 +48,8 @@ def pack_ground_truths(per_image_segments, max_gt=None):
             s = np.asarray(s)
             if s.shape != (H, W):
                 raise ValueError("image %d ground truth %d has shape %s, expected %s" % (b, g, s.shape, (H, W)))
+            if s.size and (s.min() < 0 or s.max() > 65535):
+                raise ValueError("image %d ground truth %d: labels outside 0..65535 would wrap in uint16" % (b, g))
             out[b, g] = s
     return out, n_gt
 

@@ -112,6 +112,10 @@ class metrics:
                     raise ValueError("operands could not be broadcast together with shapes %s %s"
                                      % (self.lb.shape, np.asarray(t).shape))
             G = len(self.segments_truth)
+            for t in self.segments_truth:
+                t = np.asarray(t)
+                if t.size and (t.min() < 0 or t.max() > 65535):
+                    raise ValueError("ground-truth labels must lie in 0..65535 (uint16, the dtype groundtruth.py:26 yields)")
             gts = (np.stack([np.asarray(t) for t in self.segments_truth]).astype(np.uint16)[None]
                    if G else np.zeros((1, 0, self.nx, self.ny), np.uint16))
             self._cache[size] = label_counts_host(self.lb[None].astype(np.int32), gts, dil_recall=int(size),

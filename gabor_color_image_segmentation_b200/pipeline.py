@@ -31,9 +31,13 @@ def init_indices_for(indices, n_pixels: int, k: int, seed: int = 0) -> np.ndarra
 def records_to_array(c: BatchCounts) -> np.ndarray:
     """Integer record per image as one int64 row: [n_seg, n_gt, bd, area[k], perim[k], gt_counts[G*8]]."""
     B = len(c.bd_count)
-    return np.concatenate([c.n_seg.astype(np.int64)[:, None], c.n_gt.astype(np.int64)[:, None],
-                           c.bd_count[:, None], c.area.astype(np.int64), c.perim.astype(np.int64),
-                           c.gt_counts.reshape(B, -1)], axis=1)
+    gc = np.asarray(c.gt_counts, np.int64)
+    width = int(np.prod(gc.shape[1:]))      # explicit: reshape(B, -1) cannot infer a width for an empty shard
+    return np.concatenate([c.n_seg.astype(np.int64).reshape(B, 1), c.n_gt.astype(np.int64).reshape(B, 1),
+                           np.asarray(c.bd_count, np.int64).reshape(B, 1), c.area.astype(np.int64).reshape(B, -1) if B
+                           else np.zeros((0, c.area.shape[1]), np.int64),
+                           c.perim.astype(np.int64).reshape(B, -1) if B else np.zeros((0, c.perim.shape[1]), np.int64),
+                           gc.reshape(B, width)], axis=1)
 
 
 def array_to_records(a: np.ndarray, H: int, W: int, k: int, G: int) -> BatchCounts:
@@ -99,10 +103,27 @@ def gather_records(local: np.ndarray, indices: np.ndarray, n_images: int, device
 def evaluate_batch(plan: Plan, imgs: np.ndarray, gts: np.ndarray, init_idx: np.ndarray,
                    n_gt: Optional[np.ndarray] = None, want_labels: bool = False) -> BatchCounts:
     """Host arrays in, integer records out, through the C ABI's host entry point."""
-    imgs = np.ascontiguousarray(imgs, np.uint8)
+    imgs = np.asarray(imgs)
+    gts = np.asarray(gts)
+    if imgs.dtype != np.uint8:
+        raise ValueError("imgs must be uint8 [B,H,W,3] (as imread returns them)")
+    if gts.size and (gts.min() < 0 or gts.max() > 65535):
+        raise ValueError("ground-truth labels must lie in 0..65535 (uint16, the dtype groundtruth.py:26 yields)")
+    if gts.size and int(gts.max()) + 1 > plan.n_lab_cap:
+        raise ValueError(f"a ground truth has {int(gts.max()) + 1} labels (max+1) but the plan was built with "
+                         f"n_lab_cap={plan.n_lab_cap}; build the plan with n_lab_cap >= {int(gts.max()) + 1}")
+    imgs = np.ascontiguousarray(imgs)
     gts = np.ascontiguousarray(gts, np.uint16)
     init_idx = np.ascontiguousarray(init_idx, np.int32)
     return plan.pipeline_host(imgs, gts, init_idx, imgs.shape[0], n_gt, want_labels)
+
+
+def empty_counts(plan: Plan) -> BatchCounts:
+    """Record set of an empty shard (a rank that owns no image): every collective still sees the same widths."""
+    G = max(plan.max_gt, 1)
+    z = lambda *s, dt=np.int32: np.zeros(s, dt)
+    return BatchCounts(plan.H, plan.W, z(0, dt=np.int64), z(0, G, 8, dt=np.int64), z(0, plan.k), z(0, plan.k), z(0),
+                       z(0, G), z(0), z(0))
 
 
 def dataset_scores(sums: np.ndarray) -> dict:

@@ -95,7 +95,7 @@ typedef struct gcis_config {
     int32_t max_gt;        /* ground truths per image (capacity G)          */
     int32_t n_lab_cap;     /* capacity for max(gt)+1                        */
     int32_t dil_recall;    /* `size` of set_boundary_recall (default 5)     */
-    int32_t group;         /* images per L2-resident group, 0 = auto        */
+    int32_t group;         /* images per launch group, 0 = auto (64; sized for occupancy, not for L2 residency) */
 } gcis_config;
 
 typedef struct gcis_plan gcis_plan;

@@ -6,6 +6,7 @@ import socket
 import sys
 
 import numpy as np
+import pytest
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -50,10 +51,11 @@ def _worker(rank, world, port, n_images, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_reduction_equals_single_process(tmp_path):
+@pytest.mark.parametrize("n_images", [7, 1])   # 1 image on 2 ranks: rank 1 owns an EMPTY shard and must still reach the collectives
+def test_two_rank_reduction_equals_single_process(tmp_path, n_images):
     sys.path.insert(0, ROOT)
     from gabor_color_image_segmentation_b200 import pipeline as pl
-    n_images, H, W, G, k = 7, 40, 56, 2, 5
+    H, W, G, k = 40, 56, 2, 5
     out = str(tmp_path / "r0.npy")
     mp.spawn(_worker, args=(2, _free_port(), n_images, out), nprocs=2, join=True)
     got = np.load(out, allow_pickle=True).item()

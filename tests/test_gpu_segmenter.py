@@ -156,8 +156,10 @@ def test_kmeans_ties_and_empty_clusters():
 
 def test_segment_pipeline_against_oracle():
     """End to end on synthetic 96x128 images: GPU labels vs oracle labels computed from the
-    oracle's own fp64 features.  fp32-vs-fp64 feature differences can flip near-ties, so the
-    bar is an agreement rate; the teacher-forced tests above carry the bit-exact claim."""
+    oracle's own fp64 features.  fp32-vs-fp64 feature differences can flip near-ties only: every
+    disagreeing pixel must tie within 1e-2 (relative, fp64 distances under the oracle's centroids) and
+    there may be at most 0.2 % of them; the teacher-forced tests above carry the bit-exact claim and
+    tests/test_gpu_parity_pins.py repeats this at full size."""
     torch = _torch()
     from gabor_color_image_segmentation_b200 import GaborBank, Plan
     from gabor_color_image_segmentation_b200.synth import synth_image
@@ -175,8 +177,15 @@ def test_segment_pipeline_against_oracle():
         ol, _, _ = orc.kmeans(feat[b].reshape(feat.shape[1], -1), k, T, idx[b])
         np.testing.assert_array_equal(labels[b].ravel(), ol)
         # (2) oracle end to end
-        ref_labels, _, _ = orc.segment_image(imgs[b], k, T, bank=orc.Bank.default(3, 6), init_idx=idx[b])
-        assert (ref_labels == labels[b]).mean() > 0.98
+        ref_labels, _, f64 = orc.segment_image(imgs[b], k, T, bank=orc.Bank.default(3, 6), init_idx=idx[b])
+        dis = np.flatnonzero(ref_labels.ravel() != labels[b].ravel())
+        assert len(dis) <= 2e-3 * ref_labels.size, (b, len(dis))
+        if len(dis):   # ... and whatever differs is a near-tie under the oracle's own centroids (fp64 distances)
+            prev = orc.kmeans(f64, k, T - 1, idx[b])[1].astype(np.float64)
+            X = f64[:, dis].astype(np.float64).T
+            d = np.stack([((X - prev[j]) ** 2).sum(1) for j in range(k)], 1)
+            gap = (d[np.arange(len(dis)), labels[b].ravel()[dis]] - d.min(1)) / d.min(1)
+            assert gap.max() <= 1e-2, (b, len(dis), float(gap.max()))
 
 
 def test_segmenter_slot_callable():

@@ -9,7 +9,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GCIS_LIB") or os.path.join(_PKG, "libgcis.so")
 CSRC = os.path.join(_PKG, "csrc")
-SOURCES = ["plan.cu", "gabor.cu", "kmeans.cu", "label_metrics.cu"]
+SOURCES = ["plan.cu", "gabor.cu", "gabor_tc.cu", "kmeans.cu", "label_metrics.cu"]
 
 GT_SLOTS = 8
 COLOUR = {"rgb": 0, "opponent": 1, "lab": 2}

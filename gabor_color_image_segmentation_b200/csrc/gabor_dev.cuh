@@ -1,0 +1,383 @@
+// gabor_dev.cuh — device code shared by the two filter-bank kernels (gabor.cu: both passes on the FP32 pipe;
+// gabor_tc.cu: row pass on the tcgen05 tensor cores, column pass on the FP32 pipe).
+// Reference: none (segmenter slot, BSD_metrics/script.py:30; spec in DESIGN.md section 3).
+#pragma once
+#include "gabor.cuh"
+
+namespace gcis {
+namespace gbdev {
+
+constexpr int GB_TW = 32;        // strip width = one warp of columns
+constexpr int GB_TWP = 33;       // odd stride: row-pass writes (lane = row) and column-pass reads conflict-free
+constexpr int GB_THREADS = 256;
+constexpr int GB_WARPS = GB_THREADS / 32;
+constexpr int GB_RC = 8;         // column pass: output rows per thread
+constexpr int GB_RR = 4;         // row pass: output columns per thread (32 / 4 = 8 column blocks = 8 warps)
+constexpr int GB_CHUNK = 32;     // input rows staged per row-pass step (lane = row)
+// Narrow filters (staged row <= 64 columns, i.e. half-width <= 14): 64-row chunks, two rows per lane.  The tap
+// loads are shared by the two rows and the per-chunk staging / barrier cost is paid half as often.
+constexpr int GB_CHUNK2 = 64;
+constexpr int GB_CW2 = 64;       // staged columns per row on this path
+constexpr int GB_ISTR2 = 68;     // chunk row stride: 32 n + 4 floats
+__host__ __device__ constexpr int gb_chunk_floats(int istr)
+{
+    return GB_CHUNK * istr > GB_CHUNK2 * GB_ISTR2 ? GB_CHUNK * istr : GB_CHUNK2 * GB_ISTR2;
+}
+
+struct GaborParams {
+    const float *planes;   // [B][C][H][Wp]
+    float *feat;           // [B][C*S*O][H][W]
+    const float *taps;
+    const GaborScale *scales;
+    int B, C, H, W, Wp, P, S, O, feature;
+    int feat_plane_stride;       // floats between feature planes (>= H*W)
+    int n_strips;
+    int TH[GB_MAX_SCALES];       // output rows per CTA at scale s
+    int n_vt[GB_MAX_SCALES];     // vertical tiles at scale s
+    int first_block[GB_MAX_SCALES + 1];  // block ranges ordered from the widest scale to the narrowest
+    int order[GB_MAX_SCALES];    // scale handled by range i
+    int nsrc_cap;                // rows of T the shared buffer holds
+    int istr;                    // chunk row stride: 32 n + 4 floats (aligned, conflict-free 128-bit row loads)
+    int tap_slot;                // floats reserved per staged filter (complex, interleaved) in shared memory
+    int rowtab_cap;
+};
+
+typedef unsigned long long u64;
+
+// acc.{lo,hi} += a.{lo,hi} * s: one packed FP32 FMA (fma.rn.f32x2, sm_100+), half the issue slots
+__device__ __forceinline__ void fma2_vs(u64 &acc, u64 a, float s)
+{
+    u64 b;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(s));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+// Register-blocked sliding window shared by both passes:
+//     out[i] += sum_u g[i + 2h - u] * x[u],   i < R, u < nblk*R
+// The 2R-1 taps a block of R inputs needs are re-read each block with aligned 128-bit shared
+// loads (broadcast, one wavefront each).  Complex taps are stored interleaved (re, im), so one
+// packed FMA updates the (re*x, im*x) pair of an output; with real taps and complex inputs the
+// pair is (w*xr, w*xi).
+//   CT: complex taps     CX: complex input
+//   CT &&  CX: P[i] = (A, D) += W*xr,  Q[i] = (C, B) += W*xi
+//   CT && !CX: P[i] = (A, D) += W*x
+//  !CT &&  CX: P[i] = (A, C) += w*X
+//  !CT && !CX: S[i] = A      += w*x
+// w0 points at the window of block 0; the window moves down by R taps per block.
+#ifndef GB_SWEEP_UNROLL
+#define GB_SWEEP_UNROLL 1
+#endif
+constexpr int GB_SWEEP_UNR = GB_SWEEP_UNROLL;   // pairs of blocks per unrolled step of the sweeps
+
+template <int R, bool CT, bool CX, class XLoad>
+__device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u64 (&P)[R], u64 (&Q)[R], float (&S)[R],
+                                      const float *xvec = nullptr)
+{
+    // The window of block m is taps [base - m R, base - m R + 2R): its upper half is the lower half of
+    // block m - 1, so each block loads only its R new taps (the tap loads are warp-uniform shared loads
+    // and the load pipe, not the FMA pipe, bounds the row pass) and two register halves swap roles.
+    u64 ca[CT ? R : 1], cb[CT ? R : 1];
+    float ra[CT ? 1 : R], rb[CT ? 1 : R];
+    auto load_half = [&](int m, u64 (&c)[CT ? R : 1], float (&r)[CT ? 1 : R]) {
+        if constexpr (CT) {
+            const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(w0 - (ptrdiff_t)m * 2 * R);
+#pragma unroll
+            for (int q = 0; q < R / 2; ++q) {
+                const ulonglong2 v = wp[q];
+                c[2 * q] = v.x; c[2 * q + 1] = v.y;
+            }
+        } else {
+            const float4 *wp = reinterpret_cast<const float4 *>(w0 - (ptrdiff_t)m * R);
+#pragma unroll
+            for (int q = 0; q < R / 4; ++q) {
+                const float4 v = wp[q];
+                r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+            }
+        }
+    };
+    auto block = [&](int m, const u64 (&clo)[CT ? R : 1], const u64 (&chi)[CT ? R : 1], const float (&rlo)[CT ? 1 : R],
+                     const float (&rhi)[CT ? 1 : R]) {
+        float xr[R], xi[R];
+        u64 xp[R];
+        if (R == 4 && !CX && xvec) {   // row pass: the R inputs of a block are one aligned 128-bit load
+            const float4 v = *reinterpret_cast<const float4 *>(xvec + m * 4);
+            xr[0] = v.x; xr[1 % R] = v.y; xr[2 % R] = v.z; xr[3 % R] = v.w;
+        } else {
+#pragma unroll
+            for (int uu = 0; uu < R; ++uu) xload(m * R + uu, xr[uu], xi[uu], xp[uu]);
+        }
+#pragma unroll
+        for (int uu = 0; uu < R; ++uu) {
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int t = i - uu + R - 1;
+                if constexpr (CT) {
+                    const u64 w = t < R ? clo[t % R] : chi[t % R];
+                    fma2_vs(P[i], w, xr[uu]);
+                    if constexpr (CX) fma2_vs(Q[i], w, xi[uu]);
+                } else {
+                    const float w = t < R ? rlo[t % R] : rhi[t % R];
+                    if constexpr (CX) fma2_vs(P[i], xp[uu], w);
+                    else S[i] = fmaf(w, xr[uu], S[i]);
+                }
+            }
+        }
+    };
+    load_half(-1, cb, rb);   // upper half of block 0
+#pragma unroll GB_SWEEP_UNR
+    for (int m = 0; m < nblk; m += 2) {
+        load_half(m, ca, ra);
+        block(m, ca, cb, ra, rb);
+        if (m + 1 < nblk) {
+            load_half(m + 1, cb, rb);
+            block(m + 1, cb, ca, rb, ra);
+        }
+    }
+}
+
+// Row pass of one staged chunk: lane = image row, warp = block of GB_RR output columns.
+// One tap half-window (R taps) of the row pass: R complex pairs or R real taps.
+template <bool CT>
+struct RowTaps {
+    u64 c[CT ? 4 : 1];
+    float r[CT ? 1 : 4];
+    __device__ __forceinline__ void load(const float *w0, int m)
+    {
+        if constexpr (CT) {
+            const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(w0 - (ptrdiff_t)m * 8);
+            const ulonglong2 v0 = wp[0], v1 = wp[1];
+            c[0] = v0.x; c[1] = v0.y; c[2] = v1.x; c[3] = v1.y;
+        } else {
+            const float4 v = *reinterpret_cast<const float4 *>(w0 - (ptrdiff_t)m * 4);
+            r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+        }
+    }
+};
+
+template <bool CT>
+__device__ __forceinline__ void row_pass_chunk(const float *chunk, int istr, const float *w0, int nblk, float2 *T,
+                                               int trow, bool active)
+{
+    // Software-pipelined form of sweep<4, CT, false>: the inputs and the new tap half of block m + 1 are
+    // loaded before the 16 FMAs of block m (three tap buffers rotate, two input buffers alternate), so the
+    // shared-memory latency of a block hides behind the previous block's math.  Per output the taps are
+    // applied in the same order as in sweep().
+    constexpr int R = 4;
+    static_assert(GB_RR == R, "row pass is written for 4 output columns per thread");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xb = warp * R;
+    const float *src = chunk + lane * istr + xb;
+    u64 Pv[R];
+    float Sv[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) { Pv[i] = 0ull; Sv[i] = 0.f; }
+    auto block = [&](const float4 &x4, const RowTaps<CT> &lo, const RowTaps<CT> &hi) {
+        const float x[R] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int uu = 0; uu < R; ++uu)
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int t = i - uu + R - 1;
+                if constexpr (CT) fma2_vs(Pv[i], t < R ? lo.c[t % R] : hi.c[t % R], x[uu]);
+                else Sv[i] = fmaf(t < R ? lo.r[t % R] : hi.r[t % R], x[uu], Sv[i]);
+            }
+    };
+    auto xload = [&](int m) { return *reinterpret_cast<const float4 *>(src + 4 * min(m, nblk - 1)); };
+    RowTaps<CT> A, B, C;
+    A.load(w0, -1);
+    B.load(w0, 0);
+    float4 x0 = xload(0), x1;
+    int m = 0;
+    // block m uses lo = taps(m), hi = taps(m - 1); the loads for block m + 1 are issued first
+#define GB_ROW_STEP(XC, XN, LO, HI, NX)            \
+    NX.load(w0, min(m + 1, nblk - 1));             \
+    XN = xload(m + 1);                             \
+    block(XC, LO, HI);                             \
+    if (++m >= nblk) break;
+#pragma unroll 1
+    for (;;) {
+        GB_ROW_STEP(x0, x1, B, A, C)
+        GB_ROW_STEP(x1, x0, C, B, A)
+        GB_ROW_STEP(x0, x1, A, C, B)
+        GB_ROW_STEP(x1, x0, B, A, C)
+        GB_ROW_STEP(x0, x1, C, B, A)
+        GB_ROW_STEP(x1, x0, A, C, B)
+    }
+#undef GB_ROW_STEP
+    if (active) {
+        u64 *dst = reinterpret_cast<u64 *>(T + (size_t)trow * GB_TWP + xb);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            if constexpr (CT) dst[i] = Pv[i];                      // (Tr, Ti)
+            else T[(size_t)trow * GB_TWP + xb + i] = make_float2(Sv[i], 0.f);
+        }
+    }
+}
+
+// Row pass of a 64-row chunk: lane = image rows `lane` and `lane + 32` of the chunk, warp = block of 4 output
+// columns.  Same arithmetic per output as row_pass_chunk (one FMA per tap, taps in the same order); real taps
+// update the two rows with one packed FMA.
+template <bool CT>
+__device__ __forceinline__ void row_pass_chunk2(const float *chunk, const float *w0, int nblk, float2 *T, int trow0,
+                                                int n_rows)
+{
+    constexpr int R = 4;
+    static_assert(GB_RR == R, "two-row path is written for 4 output columns per thread");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xb = warp * R;
+    const float *s0 = chunk + lane * GB_ISTR2 + xb, *s1 = s0 + 32 * GB_ISTR2;
+    u64 P0[R], P1[R];   // CT: (Tr, Ti) of row 0 / row 1;  !CT: P0[i] = (T of row 0, T of row 1)
+#pragma unroll
+    for (int i = 0; i < R; ++i) { P0[i] = 0ull; P1[i] = 0ull; }
+    u64 ca[CT ? R : 1], cb[CT ? R : 1];
+    float ra[CT ? 1 : R], rb[CT ? 1 : R];
+    auto load_half = [&](int m, u64 (&c)[CT ? R : 1], float (&r)[CT ? 1 : R]) {
+        if constexpr (CT) {
+            const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(w0 - (ptrdiff_t)m * 2 * R);
+#pragma unroll
+            for (int q = 0; q < R / 2; ++q) {
+                const ulonglong2 v = wp[q];
+                c[2 * q] = v.x; c[2 * q + 1] = v.y;
+            }
+        } else {
+            const float4 v = *reinterpret_cast<const float4 *>(w0 - (ptrdiff_t)m * R);
+            r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+        }
+    };
+    auto block = [&](int m, const u64 (&clo)[CT ? R : 1], const u64 (&chi)[CT ? R : 1], const float (&rlo)[CT ? 1 : R],
+                     const float (&rhi)[CT ? 1 : R]) {
+        const float4 v0 = *reinterpret_cast<const float4 *>(s0 + m * 4), v1 = *reinterpret_cast<const float4 *>(s1 + m * 4);
+        const float x0[R] = {v0.x, v0.y, v0.z, v0.w}, x1[R] = {v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int uu = 0; uu < R; ++uu) {
+            u64 xp = 0ull;
+            if constexpr (!CT) asm("mov.b64 %0, {%1, %2};" : "=l"(xp) : "f"(x0[uu]), "f"(x1[uu]));
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int t = i - uu + R - 1;
+                if constexpr (CT) {
+                    const u64 w = t < R ? clo[t % R] : chi[t % R];
+                    fma2_vs(P0[i], w, x0[uu]);
+                    fma2_vs(P1[i], w, x1[uu]);
+                } else {
+                    fma2_vs(P0[i], xp, t < R ? rlo[t % R] : rhi[t % R]);
+                }
+            }
+        }
+    };
+    load_half(-1, cb, rb);
+#pragma unroll GB_SWEEP_UNR
+    for (int m = 0; m < nblk; m += 2) {
+        load_half(m, ca, ra);
+        block(m, ca, cb, ra, rb);
+        if (m + 1 < nblk) {
+            load_half(m + 1, cb, rb);
+            block(m + 1, cb, ca, rb, ra);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (lane + 32 * h < n_rows) {
+            float2 *dst = T + (size_t)(trow0 + lane + 32 * h) * GB_TWP + xb;
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                if constexpr (CT) {
+                    reinterpret_cast<u64 *>(dst)[i] = h ? P1[i] : P0[i];
+                } else {
+                    float a, b;
+                    unpack2(P0[i], a, b);
+                    dst[i] = make_float2(h ? b : a, 0.f);
+                }
+            }
+        }
+    }
+}
+
+// sqrt.approx (MUFU): relative error <= 2^-22, far inside the feature tolerance; the IEEE
+// sqrtf costs a Newton fix-up and a slow-path branch per output, which was 13 % of the kernel's stall samples.
+__device__ __forceinline__ float fast_sqrt(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Column pass: lane = column of the strip, warp = blocks of GB_RC output rows.
+template <bool CX, bool CT>
+__device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, const int *rowtab, const float *w0,
+                                         int nblk, int y0, int th, int x0, float *feat0, float *feat1, int nwarps = GB_WARPS)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nrb = (th + GB_RC - 1) / GB_RC;
+    const bool col_ok = x0 + lane < P.W;
+    const u64 *Tl = reinterpret_cast<const u64 *>(T) + lane;
+    for (int rb = warp; rb < nrb; rb += nwarps) {
+        u64 Pv[GB_RC], Qv[GB_RC];
+        float Sv[GB_RC];
+#pragma unroll
+        for (int i = 0; i < GB_RC; ++i) { Pv[i] = 0ull; Qv[i] = 0ull; Sv[i] = 0.f; }
+        const int *rt = rowtab + rb * GB_RC;
+        sweep<GB_RC, CT, CX>(
+            [&](int u, float &xr, float &xi, u64 &xp) {
+                xp = Tl[rt[u]];
+                unpack2(xp, xr, xi);
+            },
+            w0, nblk, Pv, Qv, Sv);
+#pragma unroll
+        for (int i = 0; i < GB_RC; ++i) {
+            const int r = rb * GB_RC + i;
+            if (r < th && col_ok) {
+                float A, Bv = 0.f, Cv = 0.f, Dv = 0.f;
+                if constexpr (CT) {
+                    unpack2(Pv[i], A, Dv);
+                    if constexpr (CX) unpack2(Qv[i], Cv, Bv);
+                } else if constexpr (CX) {
+                    unpack2(Pv[i], A, Cv);
+                } else {
+                    A = Sv[i];
+                }
+                // theta: (A - B) + i(C + D);  pi - theta: (A + B) + i(D - C)
+                const float re0 = A - Bv, im0 = Cv + Dv;
+                const float e0 = fmaf(re0, re0, im0 * im0);
+                const size_t o = (size_t)(y0 + r) * P.W + x0 + lane;
+                feat0[o] = P.feature == GCIS_FEATURE_MAGNITUDE ? fast_sqrt(e0) : e0;
+                if (feat1) {
+                    const float re1 = A + Bv, im1 = Dv - Cv;
+                    const float e1 = fmaf(re1, re1, im1 * im1);
+                    feat1[o] = P.feature == GCIS_FEATURE_MAGNITUDE ? fast_sqrt(e1) : e1;
+                }
+            }
+        }
+    }
+}
+
+// Copy one filter's taps from the global table into shared memory in the layout sweep() reads:
+// complex -> interleaved (re, im) with tap j at complex index 1 + PAD + j (window starts land on
+// 16-byte boundaries); real -> tap j at float index sr + PAD + j.  Returns the block-0 window.
+template <int R>
+__device__ __forceinline__ const float *stage_taps(float *dst, const float *taps, int off_re, int off_im, int h, int nthr = GB_THREADS)
+{
+    const int ntap = 2 * h + 1 + 2 * GB_TAP_PAD;
+    if (off_im >= 0) {
+        for (int i = threadIdx.x; i < ntap + 2; i += nthr) {
+            const bool in = i >= 1 && i <= ntap;
+            dst[2 * i] = in ? taps[off_re + i - 1] : 0.f;
+            dst[2 * i + 1] = in ? taps[off_im + i - 1] : 0.f;
+        }
+        return dst + 2 * (GB_TAP_PAD + 2 * h + 2 - R);
+    }
+    const int sr = (4 - ((2 * h + 1) & 3)) & 3;
+    for (int i = threadIdx.x; i < ntap + sr + 4; i += nthr) {
+        const int j = i - sr;
+        dst[i] = (j >= 0 && j < ntap) ? taps[off_re + j] : 0.f;
+    }
+    return dst + sr + GB_TAP_PAD + 2 * h - R + 1;
+}
+
+
+}  // namespace gbdev
+}  // namespace gcis

@@ -1,0 +1,519 @@
+// gabor_tc.cu — filter bank with the ROW pass on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// Reference: none (segmenter slot, BSD_metrics/script.py:30; spec in DESIGN.md section 3).
+//
+// Why.  ncu on the FP32-pipe kernel (gabor.cu) shows the stage is compute bound and that its row pass, whose
+// sliding window runs along the lane-private direction, only reaches ~40 % of the FMA pipe.
+// The row pass is a small dense GEMM per 32-column strip,
+//     T[r][(c, re|im)] = sum_k  I[r][x0 - hmax + k] * Gt[(c, re|im)][k],      Gt[(c,p)][k] = g_p[c + h + hmax - k]
+// (a Toeplitz matrix of the job's complex row taps, band waste (32 + 2h) / (2h + 1) <= 1.3 for the wide scales),
+// and for the rgb colour space its data operand is EXACT in bf16: the planes hold the u8 pixel value (0..255,
+// 8 significant bits) and the 1/255 is folded into the taps.  Only the taps need splitting: g/255 = g1 + g2 + g3
+// with three bf16 terms (24 significant bits), i.e. three accumulating MMAs per K step with fp32 accumulation
+// in tensor memory.  The column pass keeps running on the FP32 pipe (it sits at ~76 % of its FMA bound and its
+// operand T would need a hi/lo split that does not fit in shared memory, profiles/r02_gabor_tc.md), but it now
+// has the SM's CUDA cores to itself: the tensor cores produce the next orientation job's T while the column
+// pass of the current one runs.
+//
+// One CTA (512 threads, 1 CTA/SM) = one 32-column strip of one (image, channel, scale), all orientation jobs:
+//   warp 14, one lane   TMA producer: per (job, 128-row block, 64-column K atom) one box of the bf16 plane
+//                       (A operand, 128 rows x 128 B, SWIZZLE_128B) and three boxes of the tap table (B operand,
+//                       64 n x 128 B each) into a 3-stage ring; completion on mbarriers.  The plane tile is the
+//                       same for every job of the scale, so it is staged from L2, never re-read from HBM.
+//   warp 15, one lane   issues tcgen05.mma.cta_group::1.kind::f16 (M = 128 rows, N = 64 = 32 columns x re|im,
+//                       K = 16 per instruction) into one of two TMEM accumulators (3 row blocks x 64 columns
+//                       each); tcgen05.commit releases ring stages and publishes finished accumulators.
+//   warps 0..13         wait for the accumulator, move it TMEM -> registers -> shared memory as the complex
+//                       intermediate T[row][33] (tcgen05.ld 32x32b), hand the accumulator back, then run the
+//                       register-blocked FFMA2 column pass of gabor_dev.cuh and the magnitude epilogue.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "async.cuh"
+#include "gabor_dev.cuh"
+
+namespace gcis {
+
+using namespace gbdev;
+
+namespace {
+
+constexpr int TC_THREADS = 512;
+constexpr int TC_COLW = 14;                    // column-pass warps (41 row blocks of 8 rows = 3 rounds of 14)
+constexpr int TC_COLT = TC_COLW * 32;
+constexpr int TC_STAGES = 3;
+constexpr int TC_MROWS = 128;                  // rows per MMA (M)
+constexpr int TC_N = 2 * GB_TW;                // 64: (column, re|im)
+constexpr int TC_KATOM = 64;                   // bf16 elements per 128-byte swizzle atom row
+constexpr int TC_A_BYTES = TC_MROWS * 128;     // 16 KB
+constexpr int TC_B_BYTES = TC_N * 128;         // 8 KB per split term
+constexpr int TC_SPLIT = 3;
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_SPLIT * TC_B_BYTES;   // 40 KB
+constexpr int TC_MAX_RB = 3;                   // row blocks per accumulator: T holds up to 384 rows
+constexpr int TC_ACC_COLS = TC_MAX_RB * TC_N;  // 192 TMEM columns per accumulator
+constexpr int TC_TMEM_COLS = 512;              // allocation (power of two >= 2 * 192)
+constexpr int TC_XFER_WARPS = 4 * TC_MAX_RB;   // warps that move TMEM -> shared memory (one per lane quadrant x row block)
+
+struct TcParams {
+    GaborParams g;                // shapes, feature tensor, FP32 tap table (column taps), scales
+    int ksteps[GB_MAX_SCALES];    // K steps of 16 per scale: ceil((32 + 2 hmax_s + kshift_s) / 16)
+    int kshift[GB_MAX_SCALES];    // (P - hmax_s) mod 8: TMA boxes must start on a 16-byte boundary of the plane row, so the K
+                                  // origin of a strip is moved left to the previous multiple of 8 columns
+    int table_row0[GB_MAX_SCALES];// first row of scale s in the B-operand table
+    int plane_rows;               // rows of the bf16 plane tensor = B * C * H
+};
+
+// instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = 64 (cute::UMMA::InstrDescriptor bit layout)
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_MROWS >> 4) << 24);
+
+// shared-memory matrix descriptor, K-major operand in the 128-byte swizzle layout the TMA boxes land in:
+// 8 rows x 128 B per swizzle atom, 1024 B between 8-row groups (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);          // start address
+    d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset
+    d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// 32 lanes x 32 consecutive 32-bit columns: lane i of the warp receives TMEM lane (quadrant base + i)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+
+// u8 pixel value -> bf16 planes with horizontal reflect padding: [B][3][H][Wp16]
+__global__ void colour_pad16_kernel(const uint8_t *__restrict__ img, __nv_bfloat16 *__restrict__ planes, int B, int H,
+                                    int W, int P, int Wp)
+{
+    const long long total = (long long)B * H * Wp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cp = (int)(i % Wp);
+        const long long br = i / Wp;
+        const int r = (int)(br % H);
+        const int b = (int)(br / H);
+        const int c = reflect_index(cp - P, W);
+        const uint8_t *px = img + (((size_t)b * H + r) * W + c) * 3;
+        const size_t plane = (size_t)H * Wp;
+        __nv_bfloat16 *dst = planes + (size_t)b * 3 * plane + (size_t)r * Wp + cp;
+        dst[0] = __ushort2bfloat16_rn(px[0]);
+        dst[plane] = __ushort2bfloat16_rn(px[1]);
+        dst[2 * plane] = __ushort2bfloat16_rn(px[2]);
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUtensorMap map_plane,
+                const __grid_constant__ CUtensorMap map_table)
+{
+    extern __shared__ unsigned char tc_smem_raw[];
+    __shared__ __align__(8) unsigned long long s_full[TC_STAGES], s_empty[TC_STAGES], s_tfull[2], s_tempty[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_lo, s_hi;
+    const GaborParams &P = Q.g;
+
+    // ---- decode the work item (same order as the FP32-pipe kernel: widest scale first) ----
+    int range = 0;
+    while (range + 1 < P.S && (int)blockIdx.x >= P.first_block[range + 1]) ++range;
+    const int s = P.order[range];
+    int rem = blockIdx.x - P.first_block[range];
+    const int nvt = P.n_vt[s];
+    const int vt = rem % nvt; rem /= nvt;
+    const int strip = rem % P.n_strips; rem /= P.n_strips;
+    const int c = rem % P.C;
+    const int b = rem / P.C;
+    const int x0 = strip * GB_TW;
+    const int y0 = vt * P.TH[s];
+    const int th = min(P.TH[s], P.H - y0);
+    const GaborScale &sc = P.scales[s];
+    const int hmax = sc.hmax, n_jobs = sc.n_jobs;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- carve shared memory: [ring of stages, 1024-byte aligned][T][column taps][row table] ----
+    const uint32_t raw = smem_u32(tc_smem_raw);
+    const uint32_t ring = (raw + 1023u) & ~1023u;
+    unsigned char *base = tc_smem_raw + (ring - raw);
+    float2 *T = reinterpret_cast<float2 *>(base + TC_STAGES * TC_STAGE_BYTES);       // [nsrc_cap][GB_TWP]
+    float *tap_col = reinterpret_cast<float *>(T + (((size_t)P.nsrc_cap * GB_TWP + 1) & ~(size_t)1));   // 16-byte aligned: 128-bit tap loads
+    int *rowtab = reinterpret_cast<int *>(tap_col + P.tap_slot);
+
+    // ---- one-time set-up ----
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_empty[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_tfull[i]), 1); mbar_init(smem_u32(&s_tempty[i]), TC_XFER_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_lo = P.H; s_hi = 0;
+    }
+    if (warp == 15) {   // tensor memory: the whole warp allocates, the address lands in shared memory
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    __syncthreads();
+    // rows of the image the column passes touch (reflect-folded) for the scale's widest job, and their span
+    const int ne = (th + GB_RC - 1) / GB_RC * GB_RC + 2 * hmax + 2 * GB_RC;
+    if (warp < TC_COLW) {
+        int lo = P.H, hi = 0;
+        for (int e = threadIdx.x; e < ne; e += TC_COLT) {
+            const int r = reflect_index(y0 - hmax + min(e, th + 2 * hmax - 1), P.H);
+            rowtab[e] = r;
+            lo = min(lo, r); hi = max(hi, r + 1);
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const int lo = s_lo, hi = s_hi;
+    const int nsrc = hi - lo;                                   // <= nsrc_cap <= 384 (host)
+    const int n_rb = (nsrc + TC_MROWS - 1) / TC_MROWS;
+    const int ksteps = Q.ksteps[s];
+    const int n_atoms = (ksteps + 3) / 4;
+    const uint32_t tmem = s_tmem;
+#ifndef TC_DEBUG
+#define TC_DEBUG 9
+#endif
+
+    if (TC_DEBUG == 0) {
+    } else if (warp == 14) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            const int gcol0 = x0 - hmax + P.P - Q.kshift[s];                 // first K column in the padded plane (multiple of 8)
+            const int prow0 = (b * P.C + c) * P.H + lo;                      // first T row in the plane tensor
+            int it = 0;
+            for (int ji = 0; ji < n_jobs; ++ji)
+                for (int rb = 0; rb < n_rb; ++rb)
+                    for (int a = 0; a < n_atoms; ++a, ++it) {
+                        const int st = it % TC_STAGES;
+                        mbar_wait(smem_u32(&s_empty[st]), ((it / TC_STAGES) & 1) ^ 1);
+                        const uint32_t fb = smem_u32(&s_full[st]);
+                        const uint32_t dst = ring + st * TC_STAGE_BYTES;
+#ifndef TC_DBG_TMA
+#define TC_DBG_TMA 3
+#endif
+                        if (TC_DBG_TMA == 0) { mbar_arrive(fb); continue; }
+                        mbar_expect_tx(fb, ((TC_DBG_TMA & 1) ? TC_A_BYTES : 0) + ((TC_DBG_TMA & 2) ? TC_SPLIT * TC_B_BYTES : 0));
+                        if (TC_DBG_TMA & 1) tma_box_2d(dst, &map_plane, gcol0 + TC_KATOM * a, prow0 + TC_MROWS * rb, fb);
+                        if (TC_DBG_TMA & 2)
+#pragma unroll
+                        for (int sp = 0; sp < TC_SPLIT; ++sp)
+                            tma_box_2d(dst + TC_A_BYTES + sp * TC_B_BYTES, &map_table, TC_KATOM * a,
+                                       Q.table_row0[s] + (ji * TC_SPLIT + sp) * TC_N, fb);
+                    }
+        }
+    } else if (warp == 15) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            int it = 0;
+            for (int ji = 0; ji < n_jobs; ++ji) {
+                const int buf = ji & 1;
+                mbar_wait(smem_u32(&s_tempty[buf]), ((ji >> 1) & 1) ^ 1);    // accumulator drained by the column warps
+                tc_fence_after();
+                for (int rb = 0; rb < n_rb; ++rb) {
+                    const uint32_t d = tmem + (uint32_t)(buf * TC_ACC_COLS + rb * TC_N);
+                    for (int a = 0; a < n_atoms; ++a, ++it) {
+                        const int st = it % TC_STAGES;
+                        mbar_wait(smem_u32(&s_full[st]), (it / TC_STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t sa = ring + st * TC_STAGE_BYTES;
+                        const uint64_t da = tc_smem_desc(sa);
+                        const int nk = min(4, ksteps - 4 * a);
+                        if (TC_DEBUG >= 2) {
+                        for (int kk = 0; kk < nk; ++kk)
+#pragma unroll
+                            for (int sp = 0; sp < TC_SPLIT; ++sp) {
+                                const uint64_t db = tc_smem_desc(sa + TC_A_BYTES + sp * TC_B_BYTES);
+                                // K advance inside the swizzle atom: 16 bf16 = 32 bytes = 2 descriptor units
+                                tc_mma(d, da + 2u * kk, db + 2u * kk, (a | kk | sp) ? 1u : 0u);
+                            }
+                        tc_commit(smem_u32(&s_empty[st]));                   // stage free once these MMAs have read it
+                        } else mbar_arrive(smem_u32(&s_empty[st]));
+                    }
+                }
+                if (TC_DEBUG >= 2) tc_commit(smem_u32(&s_tfull[buf]));       // accumulator complete
+                else mbar_arrive(smem_u32(&s_tfull[buf]));
+            }
+        }
+    } else {
+        // =============================== column-pass warps ===============================
+        const int D = P.C * P.S * P.O;
+        float *featb = P.feat + (size_t)b * D * P.feat_plane_stride;
+        // row table relative to T (shared by every job: job with half-width h starts hmax - h entries in)
+        for (int e = threadIdx.x; e < ne; e += TC_COLT) rowtab[e] = (rowtab[e] - lo) * GB_TWP;
+        for (int ji = 0; ji < n_jobs; ++ji) {
+            const GaborJob job = sc.jobs[ji];
+            const int h = job.h, buf = ji & 1;
+            const float *w_col = stage_taps<GB_RC>(tap_col, P.taps, job.col_re, job.col_im, h, TC_COLT);
+            const int nblk_col = (2 * h + GB_RC + GB_RC - 1) / GB_RC;
+            mbar_wait(smem_u32(&s_tfull[buf]), (ji >> 1) & 1);
+            tc_fence_after();
+            if (warp < TC_XFER_WARPS) {
+                const int rb = warp >> 2, q = warp & 3;
+                if (rb < n_rb && TC_DEBUG >= 3) {
+                    const int r = rb * TC_MROWS + q * 32 + lane;                 // T row of this thread
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t v[32];
+                        tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_ACC_COLS + rb * TC_N + half * 32), v);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (r < nsrc) {
+                            float2 *dst = T + (size_t)r * GB_TWP + half * 16;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) dst[j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&s_tempty[buf]));            // the tensor cores may refill it
+            }
+            named_bar_sync(1, TC_COLT);                                          // T and the column taps are in place
+            const int d0 = (c * P.S + s) * P.O;
+            float *f0 = featb + (size_t)(d0 + job.out0) * P.feat_plane_stride;
+            float *f1 = job.out1 >= 0 ? featb + (size_t)(d0 + job.out1) * P.feat_plane_stride : nullptr;
+            const int *rt = rowtab + (hmax - h);
+            const bool cx = job.row_im >= 0, ct = job.col_im >= 0;
+            if (TC_DEBUG < 4) { }
+            else if (cx && ct) col_pass<true, true>(P, T, rt, w_col, nblk_col, y0, th, x0, f0, f1, TC_COLW);
+            else if (cx) col_pass<true, false>(P, T, rt, w_col, nblk_col, y0, th, x0, f0, f1, TC_COLW);
+            else if (ct) col_pass<false, true>(P, T, rt, w_col, nblk_col, y0, th, x0, f0, f1, TC_COLW);
+            else col_pass<false, false>(P, T, rt, w_col, nblk_col, y0, th, x0, f0, f1, TC_COLW);
+            named_bar_sync(1, TC_COLT);                                          // T and the taps may be overwritten
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 15) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*tc_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int tc_encode_2d(CUtensorMap *map, const void *ptr, uint64_t cols, uint64_t rows, uint32_t box_cols, uint32_t box_rows)
+{
+    static tc_encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        GCIS_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) return set_error(GCIS_E_CUDA, "gabor: cuTensorMapEncodeTiled not available");
+        encode = reinterpret_cast<tc_encode_fn>(fn);
+    }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 2u};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(GCIS_E_CUDA, "gabor: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return GCIS_OK;
+}
+
+uint16_t bf16_rne(double v)
+{
+    const float f = (float)v;
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    const uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(r >> 16);
+}
+double bf16_value(uint16_t h)
+{
+    const uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return (double)f;
+}
+
+}  // namespace
+
+struct GaborTcPlan {
+    TcParams q;
+    size_t smem = 0;
+    int kt = 0, table_rows = 0;                // B-operand table: [table_rows][kt] bf16
+    __nv_bfloat16 *d_table = nullptr;
+    CUtensorMap map_table;
+};
+
+size_t gabor_tc_smem_bytes(int nsrc, int hmax, int th_max)
+{
+    const int tap_slot = round_up(2 * (2 * hmax + 1 + 2 * GB_TAP_PAD + 2) + 8, 4);
+    const int rowtab = round_up((th_max + GB_RC - 1) / GB_RC * GB_RC + 2 * hmax + 2 * GB_RC, 4);
+    return 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + sizeof(float2) * (((size_t)nsrc * GB_TWP + 1) & ~(size_t)1) + sizeof(float) * (size_t)tap_slot +
+           sizeof(int) * (size_t)rowtab;
+}
+
+void gabor_tc_plan_delete(GaborTcPlan *tp)
+{
+    if (!tp) return;
+    cudaFree(tp->d_table);
+    delete tp;
+}
+
+// Plan for the tensor-core path, or nullptr (with no error set) when the configuration is not covered:
+// it needs planes that are exact in bf16 (rgb: the u8 pixel value).
+GaborTcPlan *gabor_tc_plan_new(const GaborBankHost &bank, int H, int W, int C, int P, int Wp16, int feature, int colour_space)
+{
+    if (colour_space != GCIS_COLOUR_RGB) return nullptr;
+    const size_t budget = 227 * 1024;
+    const int hmax = bank.hmax;
+    if (hmax > 96) return nullptr;
+    GaborTcPlan *tp = new GaborTcPlan();
+    GaborParams &p = tp->q.g;
+    memset(&tp->q, 0, sizeof(tp->q));
+    p.C = C; p.H = H; p.W = W; p.Wp = Wp16; p.P = P; p.S = bank.S; p.O = bank.O; p.feature = feature;
+    p.n_strips = ceil_div(W, GB_TW);
+    const int cap = TC_MAX_RB * TC_MROWS;
+    int nsrc_cap;
+    if (H <= cap && gabor_tc_smem_bytes(H, hmax, H) <= budget) {
+        nsrc_cap = H;
+        for (int s = 0; s < bank.S; ++s) { p.TH[s] = H; p.n_vt[s] = 1; }
+    } else {
+        nsrc_cap = 0;
+        for (int rows = 2 * hmax + GB_RC; rows <= cap && gabor_tc_smem_bytes(rows, hmax, rows) <= budget; rows += GB_RC) nsrc_cap = rows;
+        if (nsrc_cap == 0) { delete tp; return nullptr; }
+        for (int s = 0; s < bank.S; ++s) {
+            const int hs = bank.scales[s].hmax;
+            int th = (nsrc_cap - 2 * hs) / GB_RC * GB_RC;
+            if (th < GB_RC) { delete tp; return nullptr; }
+            if (th > H) th = H;
+            p.n_vt[s] = ceil_div(H, th);
+            p.TH[s] = round_up(ceil_div(H, p.n_vt[s]), GB_RC);
+            if (p.TH[s] > th) p.TH[s] = th;
+            p.n_vt[s] = ceil_div(H, p.TH[s]);
+        }
+    }
+    int th_max = 0;
+    for (int s = 0; s < bank.S; ++s) th_max = std::max(th_max, p.TH[s]);
+    p.nsrc_cap = nsrc_cap;
+    p.tap_slot = round_up(2 * (2 * hmax + 1 + 2 * GB_TAP_PAD + 2) + 8, 4);
+    p.rowtab_cap = round_up((th_max + GB_RC - 1) / GB_RC * GB_RC + 2 * hmax + 2 * GB_RC, 4);
+    tp->smem = gabor_tc_smem_bytes(nsrc_cap, hmax, th_max);
+    std::vector<int> order(bank.S);
+    for (int s = 0; s < bank.S; ++s) order[s] = s;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bank.scales[a].hmax > bank.scales[b].hmax; });
+    for (int i = 0; i < bank.S; ++i) p.order[i] = order[i];
+
+    // ---- B-operand table: per (scale, job, split term) a [64 n][kt] bf16 matrix, n = 2 c + (re|im) ----
+    int kmax = 0, rows = 0;
+    for (int s = 0; s < bank.S; ++s) {
+        const int hs = bank.scales[s].hmax;
+        tp->q.kshift[s] = (P - hs) & 7;
+        tp->q.ksteps[s] = ceil_div(GB_TW + 2 * hs + tp->q.kshift[s], 16);
+        kmax = std::max(kmax, tp->q.ksteps[s] * 16);
+        tp->q.table_row0[s] = rows;
+        rows += bank.scales[s].n_jobs * TC_SPLIT * TC_N;
+    }
+    tp->kt = round_up(kmax, TC_KATOM);
+    tp->table_rows = rows;
+    std::vector<uint16_t> table((size_t)rows * tp->kt, 0);
+    for (int s = 0; s < bank.S; ++s) {
+        const GaborScale &sc = bank.scales[s];
+        for (int ji = 0; ji < sc.n_jobs; ++ji) {
+            const GaborJob &job = sc.jobs[ji];
+            for (int n = 0; n < TC_N; ++n) {
+                const int cc = n >> 1, part = n & 1;
+                const int off = part ? job.row_im : job.row_re;
+                if (off < 0) continue;                          // real row filter: the imaginary half stays zero
+                for (int k = 0; k < tp->q.ksteps[s] * 16; ++k) {
+                    // tap index of plane column x0 - hmax - kshift + k for output column cc
+                    const int t = cc + job.h + sc.hmax + tp->q.kshift[s] - k;
+                    if (t < 0 || t > 2 * job.h) continue;
+                    double v = (double)bank.taps[off + GB_TAP_PAD + t] / 255.0;
+                    for (int sp = 0; sp < TC_SPLIT; ++sp) {
+                        const uint16_t hb = bf16_rne(v);
+                        table[((size_t)tp->q.table_row0[s] + (ji * TC_SPLIT + sp) * TC_N + n) * tp->kt + k] = hb;
+                        v -= bf16_value(hb);
+                    }
+                }
+            }
+        }
+    }
+    if (cudaMalloc(reinterpret_cast<void **>(&tp->d_table), table.size() * 2) != cudaSuccess ||
+        cudaMemcpy(tp->d_table, table.data(), table.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+        tc_encode_2d(&tp->map_table, tp->d_table, tp->kt, rows, TC_KATOM, TC_N) != GCIS_OK) {
+        cudaGetLastError();
+        gabor_tc_plan_delete(tp);
+        return nullptr;
+    }
+    return tp;
+}
+
+size_t gabor_tc_plan_bytes(const GaborTcPlan *tp) { return tp ? (size_t)tp->table_rows * tp->kt * 2 : 0; }
+
+int colour_planes16_launch(const uint8_t *d_img, void *d_planes16, int B, int H, int W, int P, int Wp16, cudaStream_t st)
+{
+    const long long total = (long long)B * H * Wp16;
+    const int threads = 256;
+    const int blocks = (int)std::min<long long>((total + threads - 1) / threads, 148 * 16);
+    colour_pad16_kernel<<<blocks, threads, 0, st>>>(d_img, static_cast<__nv_bfloat16 *>(d_planes16), B, H, W, P, Wp16);
+    GCIS_LAUNCH_CHECK();
+    return GCIS_OK;
+}
+
+int gabor_tc_launch(GaborTcPlan &tp, const void *d_planes16, float *d_feat, const float *d_taps, const GaborScale *d_scales,
+                    int B, int feat_plane_stride, cudaStream_t st)
+{
+    GaborParams &p = tp.q.g;
+    p.planes = nullptr; p.feat = d_feat; p.taps = d_taps; p.scales = d_scales; p.B = B;
+    p.feat_plane_stride = feat_plane_stride;
+    tp.q.plane_rows = B * p.C * p.H;
+    int acc = 0;
+    for (int i = 0; i < p.S; ++i) {
+        p.first_block[i] = acc;
+        acc += B * p.C * p.n_strips * p.n_vt[p.order[i]];
+    }
+    p.first_block[p.S] = acc;
+    alignas(64) CUtensorMap map_plane;
+    const int rc = tc_encode_2d(&map_plane, d_planes16, (uint64_t)p.Wp, (uint64_t)tp.q.plane_rows, TC_KATOM, TC_MROWS);
+    if (rc) return rc;
+    static SmemAttrCache attr_cache;
+    size_t &attr_smem = attr_cache.cur();
+    if (tp.smem > attr_smem) {
+        GCIS_CUDA_TRY(cudaFuncSetAttribute(gabor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem));
+        attr_smem = tp.smem;
+    }
+    gabor_tc_kernel<<<acc, TC_THREADS, tp.smem, st>>>(tp.q, map_plane, tp.map_table);
+    GCIS_LAUNCH_CHECK();
+    return GCIS_OK;
+}
+
+}  // namespace gcis

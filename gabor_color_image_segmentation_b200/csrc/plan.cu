@@ -43,6 +43,13 @@ int kmeans_launch(const float *, size_t, int, int, int, int, int, int, int, cons
 GaborLaunchPlan *gabor_plan_new(const GaborBankHost &, int H, int W, int C, int P, int Wp, int feature, size_t *smem);
 void gabor_plan_delete(GaborLaunchPlan *);
 int gabor_launch(GaborLaunchPlan &, const float *, float *, const float *, const GaborScale *, int, int, cudaStream_t);
+// tensor-core row pass (gabor_tc.cu); plan_new returns nullptr when the configuration is not covered
+struct GaborTcPlan;
+GaborTcPlan *gabor_tc_plan_new(const GaborBankHost &, int H, int W, int C, int P, int Wp16, int feature, int colour_space);
+void gabor_tc_plan_delete(GaborTcPlan *);
+size_t gabor_tc_plan_bytes(const GaborTcPlan *);
+int colour_planes16_launch(const uint8_t *, void *, int, int, int, int, int, cudaStream_t);
+int gabor_tc_launch(GaborTcPlan &, const void *, float *, const float *, const GaborScale *, int, int, cudaStream_t);
 
 }  // namespace gcis
 
@@ -53,14 +60,15 @@ struct gcis_plan {
     std::vector<double> freqs, thetas;
     GaborBankHost bank;
     GaborLaunchPlan *glp = nullptr;
-    int D = 0, N = 0, Np = 0, P = 0, Wp = 0, group = 1;
+    GaborTcPlan *gtc = nullptr;  // non-null: the filter bank runs its row pass on the tensor cores
+    int D = 0, N = 0, Np = 0, P = 0, Wp = 0, Wp16 = 0, group = 1;
     size_t bytes = 0;
     // device workspaces
     float *d_taps = nullptr;
     GaborScale *d_scales = nullptr;
     // Two "lanes" of per-group workspaces: group g runs on lane g & 1, so the FP32-bound Gabor
     // kernel of one group overlaps the HBM-bound k-means passes of the previous one.
-    float *d_planes[2] = {nullptr, nullptr};   // [group][3][H][Wp]
+    float *d_planes[2] = {nullptr, nullptr};   // [group][3][H][Wp] f32, or [group][3][H][Wp16] bf16 on the tensor-core path
     float *d_feat[2] = {nullptr, nullptr};     // [group][D][Np]
     void *d_km_ws[2] = {nullptr, nullptr};
     cudaStream_t lane_stream[2] = {nullptr, nullptr};
@@ -142,9 +150,11 @@ int segment_group(gcis_plan *p, int lane, const uint8_t *d_img, int nb, const in
     const int pstride = d_feat_out ? p->N : p->Np;
     const bool prof = p->profiling && group_index >= 0;
     if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 0), st);
-    TRY(colour_planes_launch(d_img, p->d_planes[lane], nb, c.height, c.width, p->P, p->Wp, c.colour_space, st));
+    if (p->gtc) TRY(colour_planes16_launch(d_img, p->d_planes[lane], nb, c.height, c.width, p->P, p->Wp16, st));
+    else TRY(colour_planes_launch(d_img, p->d_planes[lane], nb, c.height, c.width, p->P, p->Wp, c.colour_space, st));
     if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 1), st);
-    TRY(gabor_launch(*p->glp, p->d_planes[lane], feat, p->d_taps, p->d_scales, nb, pstride, st));
+    if (p->gtc) TRY(gabor_tc_launch(*p->gtc, p->d_planes[lane], feat, p->d_taps, p->d_scales, nb, pstride, st));
+    else TRY(gabor_launch(*p->glp, p->d_planes[lane], feat, p->d_taps, p->d_scales, nb, pstride, st));
     if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 2), st);
     if (d_labels) {
         TRY(kmeans_launch(feat, (size_t)p->D * pstride, pstride, nb, p->D, p->N, c.k, c.iters, c.fix_shift, d_init,
@@ -259,6 +269,14 @@ int32_t gcis_plan_create(const gcis_config *cfg, gcis_plan **out)
     size_t smem = 0;
     p->glp = gabor_plan_new(p->bank, H, W, 3, p->P, p->Wp, cfg->feature, &smem);
     if (!p->glp) { delete p; return GCIS_E_INVALID; }
+    p->Wp16 = round_up(p->Wp, 8);
+    {   // GCIS_GABOR_TC=0 keeps both passes on the FP32 pipe (A/B measurements)
+        const char *e = getenv("GCIS_GABOR_TC");
+        if (!e || atoi(e) != 0) {
+            p->gtc = gabor_tc_plan_new(p->bank, H, W, 3, p->P, p->Wp16, cfg->feature, cfg->colour_space);
+            p->bytes += gabor_tc_plan_bytes(p->gtc);
+        }
+    }
 
     const size_t MB = cfg->max_batch, G = std::max(cfg->max_gt, 1), k = cfg->k;
     auto fail = [&](int code) { gcis_plan_destroy(p); return code; };
@@ -273,7 +291,8 @@ int32_t gcis_plan_create(const gcis_config *cfg, gcis_plan **out)
     if (const char *e = getenv("GCIS_LANES")) p->n_lanes = atoi(e) >= 2 ? 2 : 1;
     if (cfg->max_batch <= p->group) p->n_lanes = 1;
     for (int l = 0; l < p->n_lanes; ++l) {
-        PA(p->d_planes[l], (size_t)p->group * 3 * H * p->Wp);
+        // f32 planes, or bf16 planes (half the bytes) when the tensor cores take the row pass
+        PA(p->d_planes[l], p->gtc ? ((size_t)p->group * 3 * H * p->Wp16 + 1) / 2 : (size_t)p->group * 3 * H * p->Wp);
         PA(p->d_feat[l], (size_t)p->group * p->D * p->Np);
         char *ws = nullptr;
         int rc2 = dev_alloc(&ws, kmeans_workspace_bytes(p->group, p->D, p->N, cfg->k), &p->bytes);
@@ -335,6 +354,7 @@ void gcis_plan_destroy(gcis_plan *p)
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     if (p->stream) cudaStreamDestroy(p->stream);
     gabor_plan_delete(p->glp);
+    gabor_tc_plan_delete(p->gtc);
     delete p;
 }
 

@@ -355,6 +355,15 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
     }
 }
 
+// Block-0 window of a filter that stage_taps() already copied to `dst` (same arithmetic as its return value).
+template <int R>
+__device__ __forceinline__ const float *stage_taps_window(const float *dst, int off_im, int h)
+{
+    if (off_im >= 0) return dst + 2 * (GB_TAP_PAD + 2 * h + 2 - R);
+    const int sr = (4 - ((2 * h + 1) & 3)) & 3;
+    return dst + sr + GB_TAP_PAD + 2 * h - R + 1;
+}
+
 // Copy one filter's taps from the global table into shared memory in the layout sweep() reads:
 // complex -> interleaved (re, im) with tap j at complex index 1 + PAD + j (window starts land on
 // 16-byte boundaries); real -> tap j at float index sr + PAD + j.  Returns the block-0 window.

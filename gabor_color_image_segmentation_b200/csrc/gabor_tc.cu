@@ -28,6 +28,7 @@
 //                       register-blocked FFMA2 column pass of gabor_dev.cuh and the magnitude epilogue.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -41,9 +42,13 @@ using namespace gbdev;
 
 namespace {
 
-constexpr int TC_THREADS = 512;
-constexpr int TC_COLW = 14;                    // column-pass warps (41 row blocks of 8 rows = 3 rounds of 14)
+#ifndef TC_COLW_N
+#define TC_COLW_N 16
+#endif
+constexpr int TC_COLW = TC_COLW_N;             // column-pass warps: 4 per SM sub-partition
 constexpr int TC_COLT = TC_COLW * 32;
+constexpr int TC_TMA_WARP = TC_COLW, TC_MMA_WARP = TC_COLW + 1;
+constexpr int TC_THREADS = TC_COLT + 64;
 constexpr int TC_STAGES = 3;
 constexpr int TC_MROWS = 128;                  // rows per MMA (M)
 constexpr int TC_N = 2 * GB_TW;                // 64: (column, re|im)
@@ -63,6 +68,8 @@ struct TcParams {
     int kshift[GB_MAX_SCALES];    // (P - hmax_s) mod 8: TMA boxes must start on a 16-byte boundary of the plane row, so the K
                                   // origin of a strip is moved left to the previous multiple of 8 columns
     int table_row0[GB_MAX_SCALES];// first row of scale s in the B-operand table
+    int hmax[GB_MAX_SCALES], n_jobs[GB_MAX_SCALES];   // copies of the scale table for the single-thread roles
+    int max_jobs;                 // jobs of the scale with the most jobs (column-tap slots in shared memory)
     int plane_rows;               // rows of the bf16 plane tensor = B * C * H
 };
 
@@ -134,6 +141,56 @@ __global__ void colour_pad16_kernel(const uint8_t *__restrict__ img, __nv_bfloat
     }
 }
 
+#ifdef TC_TRACE   // timing experiment only: per-CTA cycles per phase of the column warps (thread 0)
+constexpr int TC_TR_CTAS = 8192;
+__device__ long long tc_trace_buf[TC_TR_CTAS][8];
+#define TC_TR_DECL long long tr_t = clock64(), tr_acc[6] = {0, 0, 0, 0, 0, 0}; const long long tr_t0 = tr_t
+#define TC_TR_ADD(slot) do { const long long n_ = clock64(); tr_acc[slot] += n_ - tr_t; tr_t = n_; } while (0)
+#else
+#define TC_TR_DECL do { } while (0)
+#define TC_TR_ADD(slot) do { } while (0)
+#endif
+
+// One work item = one 32-column strip of one (image, channel, scale): decoded identically by every role.
+struct TcItem {
+    int s, b, c, x0, y0, th, hmax, n_jobs, lo, nsrc, n_rb, ksteps, n_atoms;
+};
+
+__device__ __forceinline__ TcItem tc_decode(const TcParams &Q, int item)
+{
+    const GaborParams &P = Q.g;
+    TcItem it;
+    int range = 0;
+    while (range + 1 < P.S && item >= P.first_block[range + 1]) ++range;   // ranges are ordered widest scale first
+    it.s = P.order[range];
+    int rem = item - P.first_block[range];
+    const int nvt = P.n_vt[it.s];
+    const int vt = rem % nvt; rem /= nvt;
+    const int strip = rem % P.n_strips; rem /= P.n_strips;
+    it.c = rem % P.C;
+    it.b = rem / P.C;
+    it.x0 = strip * GB_TW;
+    it.y0 = vt * P.TH[it.s];
+    it.th = min(P.TH[it.s], P.H - it.y0);
+    it.hmax = Q.hmax[it.s];
+    it.n_jobs = Q.n_jobs[it.s];
+    // image rows the column passes of this tile touch after reflect folding: [lo, lo + nsrc)
+    const int a = it.y0 - it.hmax, e = it.y0 + it.th + it.hmax;
+    int lo = a < 0 ? 0 : a, hi = e > P.H ? P.H : e;
+    if (e > P.H) lo = min(lo, max(0, 2 * P.H - e));
+    if (a < 0) hi = max(hi, min(P.H, -a));
+    if (-a > P.H || e - P.H > P.H) { lo = 0; hi = P.H; }
+    it.lo = lo;
+    it.nsrc = hi - lo;                                   // <= nsrc_cap <= 384 (host)
+    it.n_rb = (it.nsrc + TC_MROWS - 1) / TC_MROWS;
+    it.ksteps = Q.ksteps[it.s];
+    it.n_atoms = (it.ksteps + 3) / 4;
+    return it;
+}
+
+// Persistent kernel: one CTA per SM walks the work items i = blockIdx.x, blockIdx.x + gridDim.x, ...; the
+// orientation jobs of consecutive items form one stream through the TMA ring and the two TMEM accumulators,
+// so the tensor cores already work on the next item while the column warps finish the current one.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUtensorMap map_plane,
                 const __grid_constant__ CUtensorMap map_table)
@@ -141,182 +198,167 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
     extern __shared__ unsigned char tc_smem_raw[];
     __shared__ __align__(8) unsigned long long s_full[TC_STAGES], s_empty[TC_STAGES], s_tfull[2], s_tempty[2];
     __shared__ uint32_t s_tmem;
-    __shared__ int s_lo, s_hi;
     const GaborParams &P = Q.g;
-
-    // ---- decode the work item (same order as the FP32-pipe kernel: widest scale first) ----
-    int range = 0;
-    while (range + 1 < P.S && (int)blockIdx.x >= P.first_block[range + 1]) ++range;
-    const int s = P.order[range];
-    int rem = blockIdx.x - P.first_block[range];
-    const int nvt = P.n_vt[s];
-    const int vt = rem % nvt; rem /= nvt;
-    const int strip = rem % P.n_strips; rem /= P.n_strips;
-    const int c = rem % P.C;
-    const int b = rem / P.C;
-    const int x0 = strip * GB_TW;
-    const int y0 = vt * P.TH[s];
-    const int th = min(P.TH[s], P.H - y0);
-    const GaborScale &sc = P.scales[s];
-    const int hmax = sc.hmax, n_jobs = sc.n_jobs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_items = P.first_block[P.S];
 
-    // ---- carve shared memory: [ring of stages, 1024-byte aligned][T][column taps][row table] ----
+    // ---- carve shared memory: [ring of stages, 1024-byte aligned][T][column taps of every job][row table] ----
     const uint32_t raw = smem_u32(tc_smem_raw);
     const uint32_t ring = (raw + 1023u) & ~1023u;
     unsigned char *base = tc_smem_raw + (ring - raw);
     float2 *T = reinterpret_cast<float2 *>(base + TC_STAGES * TC_STAGE_BYTES);       // [nsrc_cap][GB_TWP]
     float *tap_col = reinterpret_cast<float *>(T + (((size_t)P.nsrc_cap * GB_TWP + 1) & ~(size_t)1));   // 16-byte aligned: 128-bit tap loads
-    int *rowtab = reinterpret_cast<int *>(tap_col + P.tap_slot);
+    int *rowtab = reinterpret_cast<int *>(tap_col + (size_t)Q.max_jobs * P.tap_slot);
 
+    TC_TR_DECL;
     // ---- one-time set-up ----
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_STAGES; ++i) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_empty[i]), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_tfull[i]), 1); mbar_init(smem_u32(&s_tempty[i]), TC_XFER_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_lo = P.H; s_hi = 0;
     }
-    if (warp == 15) {   // tensor memory: the whole warp allocates, the address lands in shared memory
+    if (warp == TC_MMA_WARP) {   // tensor memory: the whole warp allocates, the address lands in shared memory
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TC_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    __syncthreads();
-    // rows of the image the column passes touch (reflect-folded) for the scale's widest job, and their span
-    const int ne = (th + GB_RC - 1) / GB_RC * GB_RC + 2 * hmax + 2 * GB_RC;
-    if (warp < TC_COLW) {
-        int lo = P.H, hi = 0;
-        for (int e = threadIdx.x; e < ne; e += TC_COLT) {
-            const int r = reflect_index(y0 - hmax + min(e, th + 2 * hmax - 1), P.H);
-            rowtab[e] = r;
-            lo = min(lo, r); hi = max(hi, r + 1);
-        }
-        lo = __reduce_min_sync(0xffffffffu, lo);
-        hi = __reduce_max_sync(0xffffffffu, hi);
-        if (lane == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const int lo = s_lo, hi = s_hi;
-    const int nsrc = hi - lo;                                   // <= nsrc_cap <= 384 (host)
-    const int n_rb = (nsrc + TC_MROWS - 1) / TC_MROWS;
-    const int ksteps = Q.ksteps[s];
-    const int n_atoms = (ksteps + 3) / 4;
     const uint32_t tmem = s_tmem;
-#ifndef TC_DEBUG
-#define TC_DEBUG 9
-#endif
 
-    if (TC_DEBUG == 0) {
-    } else if (warp == 14) {
+    if (warp == TC_TMA_WARP) {
         // =============================== TMA producer ===============================
         if (lane == 0) {
-            const int gcol0 = x0 - hmax + P.P - Q.kshift[s];                 // first K column in the padded plane (multiple of 8)
-            const int prow0 = (b * P.C + c) * P.H + lo;                      // first T row in the plane tensor
             int it = 0;
-            for (int ji = 0; ji < n_jobs; ++ji)
-                for (int rb = 0; rb < n_rb; ++rb)
-                    for (int a = 0; a < n_atoms; ++a, ++it) {
-                        const int st = it % TC_STAGES;
-                        mbar_wait(smem_u32(&s_empty[st]), ((it / TC_STAGES) & 1) ^ 1);
-                        const uint32_t fb = smem_u32(&s_full[st]);
-                        const uint32_t dst = ring + st * TC_STAGE_BYTES;
-#ifndef TC_DBG_TMA
-#define TC_DBG_TMA 3
-#endif
-                        if (TC_DBG_TMA == 0) { mbar_arrive(fb); continue; }
-                        mbar_expect_tx(fb, ((TC_DBG_TMA & 1) ? TC_A_BYTES : 0) + ((TC_DBG_TMA & 2) ? TC_SPLIT * TC_B_BYTES : 0));
-                        if (TC_DBG_TMA & 1) tma_box_2d(dst, &map_plane, gcol0 + TC_KATOM * a, prow0 + TC_MROWS * rb, fb);
-                        if (TC_DBG_TMA & 2)
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const TcItem w = tc_decode(Q, item);
+                const int gcol0 = w.x0 - w.hmax + P.P - Q.kshift[w.s];       // first K column in the padded plane (multiple of 8)
+                const int prow0 = (w.b * P.C + w.c) * P.H + w.lo;            // first T row in the plane tensor
+                for (int ji = 0; ji < w.n_jobs; ++ji)
+                    for (int rb = 0; rb < w.n_rb; ++rb)
+                        for (int a = 0; a < w.n_atoms; ++a, ++it) {
+                            const int st = it % TC_STAGES;
+                            mbar_wait(smem_u32(&s_empty[st]), ((it / TC_STAGES) & 1) ^ 1);
+                            const uint32_t fb = smem_u32(&s_full[st]);
+                            const uint32_t dst = ring + st * TC_STAGE_BYTES;
+                            mbar_expect_tx(fb, TC_STAGE_BYTES);
+                            tma_box_2d(dst, &map_plane, gcol0 + TC_KATOM * a, prow0 + TC_MROWS * rb, fb);
 #pragma unroll
-                        for (int sp = 0; sp < TC_SPLIT; ++sp)
-                            tma_box_2d(dst + TC_A_BYTES + sp * TC_B_BYTES, &map_table, TC_KATOM * a,
-                                       Q.table_row0[s] + (ji * TC_SPLIT + sp) * TC_N, fb);
-                    }
+                            for (int sp = 0; sp < TC_SPLIT; ++sp)
+                                tma_box_2d(dst + TC_A_BYTES + sp * TC_B_BYTES, &map_table, TC_KATOM * a,
+                                           Q.table_row0[w.s] + (ji * TC_SPLIT + sp) * TC_N, fb);
+                        }
+            }
         }
-    } else if (warp == 15) {
+    } else if (warp == TC_MMA_WARP) {
         // =============================== MMA issuer ===============================
         if (lane == 0) {
-            int it = 0;
-            for (int ji = 0; ji < n_jobs; ++ji) {
-                const int buf = ji & 1;
-                mbar_wait(smem_u32(&s_tempty[buf]), ((ji >> 1) & 1) ^ 1);    // accumulator drained by the column warps
-                tc_fence_after();
-                for (int rb = 0; rb < n_rb; ++rb) {
-                    const uint32_t d = tmem + (uint32_t)(buf * TC_ACC_COLS + rb * TC_N);
-                    for (int a = 0; a < n_atoms; ++a, ++it) {
-                        const int st = it % TC_STAGES;
-                        mbar_wait(smem_u32(&s_full[st]), (it / TC_STAGES) & 1);
-                        tc_fence_after();
-                        const uint32_t sa = ring + st * TC_STAGE_BYTES;
-                        const uint64_t da = tc_smem_desc(sa);
-                        const int nk = min(4, ksteps - 4 * a);
-                        if (TC_DEBUG >= 2) {
-                        for (int kk = 0; kk < nk; ++kk)
+            int it = 0, jg = 0;   // ring step and job counter over the whole item stream
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const TcItem w = tc_decode(Q, item);
+                for (int ji = 0; ji < w.n_jobs; ++ji, ++jg) {
+                    const int buf = jg & 1;
+                    mbar_wait(smem_u32(&s_tempty[buf]), ((jg >> 1) & 1) ^ 1);    // accumulator drained by the column warps
+                    tc_fence_after();
+                    for (int rb = 0; rb < w.n_rb; ++rb) {
+                        const uint32_t d = tmem + (uint32_t)(buf * TC_ACC_COLS + rb * TC_N);
+                        for (int a = 0; a < w.n_atoms; ++a, ++it) {
+                            const int st = it % TC_STAGES;
+                            mbar_wait(smem_u32(&s_full[st]), (it / TC_STAGES) & 1);
+                            tc_fence_after();
+                            const uint32_t sa = ring + st * TC_STAGE_BYTES;
+                            const uint64_t da = tc_smem_desc(sa);
+                            const int nk = min(4, w.ksteps - 4 * a);
+                            for (int kk = 0; kk < nk; ++kk)
 #pragma unroll
-                            for (int sp = 0; sp < TC_SPLIT; ++sp) {
-                                const uint64_t db = tc_smem_desc(sa + TC_A_BYTES + sp * TC_B_BYTES);
-                                // K advance inside the swizzle atom: 16 bf16 = 32 bytes = 2 descriptor units
-                                tc_mma(d, da + 2u * kk, db + 2u * kk, (a | kk | sp) ? 1u : 0u);
-                            }
-                        tc_commit(smem_u32(&s_empty[st]));                   // stage free once these MMAs have read it
-                        } else mbar_arrive(smem_u32(&s_empty[st]));
-                    }
-                }
-                if (TC_DEBUG >= 2) tc_commit(smem_u32(&s_tfull[buf]));       // accumulator complete
-                else mbar_arrive(smem_u32(&s_tfull[buf]));
-            }
-        }
-    } else {
-        // =============================== column-pass warps ===============================
-        const int D = P.C * P.S * P.O;
-        float *featb = P.feat + (size_t)b * D * P.feat_plane_stride;
-        // row table relative to T (shared by every job: job with half-width h starts hmax - h entries in)
-        for (int e = threadIdx.x; e < ne; e += TC_COLT) rowtab[e] = (rowtab[e] - lo) * GB_TWP;
-        for (int ji = 0; ji < n_jobs; ++ji) {
-            const GaborJob job = sc.jobs[ji];
-            const int h = job.h, buf = ji & 1;
-            const float *w_col = stage_taps<GB_RC>(tap_col, P.taps, job.col_re, job.col_im, h, TC_COLT);
-            const int nblk_col = (2 * h + GB_RC + GB_RC - 1) / GB_RC;
-            mbar_wait(smem_u32(&s_tfull[buf]), (ji >> 1) & 1);
-            tc_fence_after();
-            if (warp < TC_XFER_WARPS) {
-                const int rb = warp >> 2, q = warp & 3;
-                if (rb < n_rb && TC_DEBUG >= 3) {
-                    const int r = rb * TC_MROWS + q * 32 + lane;                 // T row of this thread
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        uint32_t v[32];
-                        tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_ACC_COLS + rb * TC_N + half * 32), v);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (r < nsrc) {
-                            float2 *dst = T + (size_t)r * GB_TWP + half * 16;
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) dst[j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                                for (int sp = 0; sp < TC_SPLIT; ++sp) {
+                                    const uint64_t db = tc_smem_desc(sa + TC_A_BYTES + sp * TC_B_BYTES);
+                                    // K advance inside the swizzle atom: 16 bf16 = 32 bytes = 2 descriptor units
+                                    tc_mma(d, da + 2u * kk, db + 2u * kk, (a | kk | sp) ? 1u : 0u);
+                                }
+                            tc_commit(smem_u32(&s_empty[st]));                   // stage free once these MMAs have read it
                         }
                     }
+                    tc_commit(smem_u32(&s_tfull[buf]));                          // accumulator complete
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&s_tempty[buf]));            // the tensor cores may refill it
             }
-            named_bar_sync(1, TC_COLT);                                          // T and the column taps are in place
-            const int d0 = (c * P.S + s) * P.O;
-            float *f0 = featb + (size_t)(d0 + job.out0) * P.feat_plane_stride;
-            float *f1 = job.out1 >= 0 ? featb + (size_t)(d0 + job.out1) * P.feat_plane_stride : nullptr;
-            const int *rt = rowtab + (hmax - h);
-            const bool cx = job.row_im >= 0, ct = job.col_im >= 0;
-            if (TC_DEBUG < 4) { }
-            else if (cx && ct) col_pass<true, true>(P, T, rt, w_col, nblk_col, y0, th, x0, f0, f1, TC_COLW);
-            else if (cx) col_pass<true, false>(P, T, rt, w_col, nblk_col, y0, th, x0, f0, f1, TC_COLW);
-            else if (ct) col_pass<false, true>(P, T, rt, w_col, nblk_col, y0, th, x0, f0, f1, TC_COLW);
-            else col_pass<false, false>(P, T, rt, w_col, nblk_col, y0, th, x0, f0, f1, TC_COLW);
-            named_bar_sync(1, TC_COLT);                                          // T and the taps may be overwritten
         }
+    } else if (warp < TC_COLW) {
+        // =============================== column-pass warps ===============================
+        const int D = P.C * P.S * P.O;
+        int jg = 0, cur_s = -1, cur_y0 = -1;
+        TC_TR_ADD(0);
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const TcItem w = tc_decode(Q, item);
+            const GaborScale &sc = P.scales[w.s];
+            float *featb = P.feat + (size_t)w.b * D * P.feat_plane_stride;
+            if (w.s != cur_s || w.y0 != cur_y0) {
+                // (the trailing barrier of the previous job guarantees nobody still reads the tables)
+                // row table relative to T for the scale's widest job (a job with half-width h starts hmax - h entries in)
+                const int ne = (w.th + GB_RC - 1) / GB_RC * GB_RC + 2 * w.hmax + 2 * GB_RC;
+                for (int e = threadIdx.x; e < ne; e += TC_COLT)
+                    rowtab[e] = (reflect_index(w.y0 - w.hmax + min(e, w.th + 2 * w.hmax - 1), P.H) - w.lo) * GB_TWP;
+                if (w.s != cur_s)   // column taps of every job of the scale
+                    for (int ji = 0; ji < w.n_jobs; ++ji)
+                        stage_taps<GB_RC>(tap_col + (size_t)ji * P.tap_slot, P.taps, sc.jobs[ji].col_re, sc.jobs[ji].col_im, sc.jobs[ji].h, TC_COLT);
+                cur_s = w.s; cur_y0 = w.y0;
+            }
+            TC_TR_ADD(4);
+            for (int ji = 0; ji < w.n_jobs; ++ji, ++jg) {
+                const GaborJob job = sc.jobs[ji];
+                const int h = job.h, buf = jg & 1;
+                const float *w_col = stage_taps_window<GB_RC>(tap_col + (size_t)ji * P.tap_slot, job.col_im, h);
+                const int nblk_col = (2 * h + GB_RC + GB_RC - 1) / GB_RC;
+                mbar_wait(smem_u32(&s_tfull[buf]), (jg >> 1) & 1);
+                tc_fence_after();
+                TC_TR_ADD(1);
+                if (warp < TC_XFER_WARPS) {
+                    const int rb = warp >> 2, q = warp & 3;
+                    if (rb < w.n_rb) {
+                        const int r = rb * TC_MROWS + q * 32 + lane;                 // T row of this thread
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            uint32_t v[32];
+                            tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_ACC_COLS + rb * TC_N + half * 32), v);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                            if (r < w.nsrc) {
+                                float2 *dst = T + (size_t)r * GB_TWP + half * 16;
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) dst[j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&s_tempty[buf]));            // the tensor cores may refill it
+                }
+                named_bar_sync(1, TC_COLT);                                          // T (and the tables) are in place
+                TC_TR_ADD(2);
+                const int d0 = (w.c * P.S + w.s) * P.O;
+                float *f0 = featb + (size_t)(d0 + job.out0) * P.feat_plane_stride;
+                float *f1 = job.out1 >= 0 ? featb + (size_t)(d0 + job.out1) * P.feat_plane_stride : nullptr;
+                const int *rt = rowtab + (w.hmax - h);
+                const bool cx = job.row_im >= 0, ct = job.col_im >= 0;
+                if (cx && ct) col_pass<true, true>(P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW);
+                else if (cx) col_pass<true, false>(P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW);
+                else if (ct) col_pass<false, true>(P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW);
+                else col_pass<false, false>(P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW);
+                TC_TR_ADD(3);
+                named_bar_sync(1, TC_COLT);                                          // T may be overwritten
+                TC_TR_ADD(5);
+            }
+        }
+#ifdef TC_TRACE
+        if (threadIdx.x == 0 && blockIdx.x < TC_TR_CTAS) {
+            long long *o = tc_trace_buf[blockIdx.x];
+            for (int i = 0; i < 6; ++i) o[i] = tr_acc[i];
+            o[6] = clock64() - tr_t0; o[7] = 0;
+        }
+#endif
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 15) {
+    if (warp == TC_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
     }
@@ -373,11 +415,11 @@ struct GaborTcPlan {
     CUtensorMap map_table;
 };
 
-size_t gabor_tc_smem_bytes(int nsrc, int hmax, int th_max)
+size_t gabor_tc_smem_bytes(int nsrc, int hmax, int th_max, int max_jobs)
 {
     const int tap_slot = round_up(2 * (2 * hmax + 1 + 2 * GB_TAP_PAD + 2) + 8, 4);
     const int rowtab = round_up((th_max + GB_RC - 1) / GB_RC * GB_RC + 2 * hmax + 2 * GB_RC, 4);
-    return 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + sizeof(float2) * (((size_t)nsrc * GB_TWP + 1) & ~(size_t)1) + sizeof(float) * (size_t)tap_slot +
+    return 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + sizeof(float2) * (((size_t)nsrc * GB_TWP + 1) & ~(size_t)1) + sizeof(float) * (size_t)tap_slot * max_jobs +
            sizeof(int) * (size_t)rowtab;
 }
 
@@ -402,13 +444,20 @@ GaborTcPlan *gabor_tc_plan_new(const GaborBankHost &bank, int H, int W, int C, i
     p.C = C; p.H = H; p.W = W; p.Wp = Wp16; p.P = P; p.S = bank.S; p.O = bank.O; p.feature = feature;
     p.n_strips = ceil_div(W, GB_TW);
     const int cap = TC_MAX_RB * TC_MROWS;
+    int max_jobs = 1;
+    for (int s = 0; s < bank.S; ++s) {
+        max_jobs = std::max(max_jobs, bank.scales[s].n_jobs);
+        tp->q.hmax[s] = bank.scales[s].hmax;
+        tp->q.n_jobs[s] = bank.scales[s].n_jobs;
+    }
+    tp->q.max_jobs = max_jobs;
     int nsrc_cap;
-    if (H <= cap && gabor_tc_smem_bytes(H, hmax, H) <= budget) {
+    if (H <= cap && gabor_tc_smem_bytes(H, hmax, H, max_jobs) <= budget) {
         nsrc_cap = H;
         for (int s = 0; s < bank.S; ++s) { p.TH[s] = H; p.n_vt[s] = 1; }
     } else {
         nsrc_cap = 0;
-        for (int rows = 2 * hmax + GB_RC; rows <= cap && gabor_tc_smem_bytes(rows, hmax, rows) <= budget; rows += GB_RC) nsrc_cap = rows;
+        for (int rows = 2 * hmax + GB_RC; rows <= cap && gabor_tc_smem_bytes(rows, hmax, rows, max_jobs) <= budget; rows += GB_RC) nsrc_cap = rows;
         if (nsrc_cap == 0) { delete tp; return nullptr; }
         for (int s = 0; s < bank.S; ++s) {
             const int hs = bank.scales[s].hmax;
@@ -426,7 +475,7 @@ GaborTcPlan *gabor_tc_plan_new(const GaborBankHost &bank, int H, int W, int C, i
     p.nsrc_cap = nsrc_cap;
     p.tap_slot = round_up(2 * (2 * hmax + 1 + 2 * GB_TAP_PAD + 2) + 8, 4);
     p.rowtab_cap = round_up((th_max + GB_RC - 1) / GB_RC * GB_RC + 2 * hmax + 2 * GB_RC, 4);
-    tp->smem = gabor_tc_smem_bytes(nsrc_cap, hmax, th_max);
+    tp->smem = gabor_tc_smem_bytes(nsrc_cap, hmax, th_max, max_jobs);
     std::vector<int> order(bank.S);
     for (int s = 0; s < bank.S; ++s) order[s] = s;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bank.scales[a].hmax > bank.scales[b].hmax; });
@@ -511,9 +560,26 @@ int gabor_tc_launch(GaborTcPlan &tp, const void *d_planes16, float *d_feat, cons
         GCIS_CUDA_TRY(cudaFuncSetAttribute(gabor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem));
         attr_smem = tp.smem;
     }
-    gabor_tc_kernel<<<acc, TC_THREADS, tp.smem, st>>>(tp.q, map_plane, tp.map_table);
+    static const int n_sm = [] {
+        int dev = 0, n = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n > 0 ? n : 148;
+    }();
+    // GCIS_GABOR_SMS=n: run the persistent kernel on n SMs only, leaving the others to the HBM-bound k-means passes of
+    // the previous image group that the second lane runs concurrently (plan.cu)
+    static const int sm_cap = [] { const char *e = getenv("GCIS_GABOR_SMS"); return e ? atoi(e) : 0; }();
+    const int grid = std::min(acc, sm_cap > 0 ? std::min(sm_cap, n_sm) : n_sm);
+    gabor_tc_kernel<<<grid, TC_THREADS, tp.smem, st>>>(tp.q, map_plane, tp.map_table);
     GCIS_LAUNCH_CHECK();
     return GCIS_OK;
 }
 
 }  // namespace gcis
+
+#ifdef TC_TRACE
+extern "C" __attribute__((visibility("default"))) int gcis_tc_trace_read(long long *out, size_t bytes)
+{
+    return (int)cudaMemcpyFromSymbol(out, gcis::tc_trace_buf, bytes);
+}
+#endif

@@ -9,7 +9,8 @@ A step = one pass of the whole path over one batch of `--images` images per GPU 
 configs[1]: a 200-image BSDS-test-shaped batch).  Weak scaling: every rank processes its own batch.
   value  : images/s with inputs already resident in HBM (device timing, CUDA events, max over ranks)
   e2e    : images/s through the C ABI's host entry point (pinned host buffers in, records out)
-The oracle (oracle/) is executed only for the cpu_baseline / --impl reference legs.
+The oracle (oracle/) and oracle/_ref (the reference's own metrics.py, copied there by build()) are executed only
+for the cpu_baseline / --impl reference legs (benchmarks/cpu_baselines.py).
 """
 import argparse
 import json
@@ -141,6 +142,10 @@ def run_reference(args):
         r, dt = cpu_pipeline_rate(sample, threads)
         rates.append(r); secs.append(dt)
     value = sample * len(secs) / sum(secs)
+    extra = {}
+    if not args.no_ref_metrics:
+        from benchmarks import cpu_baselines
+        extra = cpu_baselines.measure(threads)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -148,7 +153,7 @@ def run_reference(args):
                        "images_per_step": sample},
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
                              "sample": "%d images per step, one image per host thread, C oracle "
-                                       "(fp64 separable Gabor + fp32-exact k-means + metrics)" % sample},
+                                       "(fp64 separable Gabor + fp32-exact k-means + metrics)" % sample, **extra},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -181,6 +186,8 @@ def run_gpu(args):
     idx = init_indices_for(range(rank * B, rank * B + B), H * W, K_CLUSTERS)
 
     plan = Plan(H, W, max_batch=B, k=K_CLUSTERS, iters=ITERS, max_gt=G, n_lab_cap=64, group=args.group)
+    launch_group = plan.launch_group(B)          # images per kernel launch (200 -> 4 launches of 50)
+    uses_tc = plan.uses_tensor_cores
     d_img = torch.from_numpy(imgs).to(dev)
     d_gt = torch.from_numpy(gts.view(np.int16)).to(dev)
     d_idx = torch.from_numpy(idx).to(dev)
@@ -252,6 +259,8 @@ def run_gpu(args):
     plan1.fetch()
     stage = plan1.last_stage_ms()
     plan1.close()
+    os.environ.pop("GCIS_LANES", None)
+    latency = one_image_latency(imgs[0], gts[0]) if rank == 0 else None
 
     if rank == 0:
         peaks = {}
@@ -270,19 +279,34 @@ def run_gpu(args):
         gb_tfs = gabor_flop / (stage["gabor"] * 1e-3) / 1e12
         total_imgs = B * world * args.steps
         dominant = "kmeans" if stage["kmeans"] >= stage["gabor"] else "gabor"
-        group = args.group or 64
-        # DRAM bytes per launch from the committed ncu capture (profiles/r01_launches.csv: 16-image
-        # launches, read+write, mean over the 20 passes of a group), scaled to this run's launch size
-        traffic_per_image_pass = 44.7e6
-        roof_km = {"kernel": "km_tile_kernel<8,256,2> (%d launches per %d-image group, timed with their km_finalize_kernel)"
-                             % (ITERS, group), "bound": "hbm",
+        # DRAM bytes of ONE km_tile_kernel launch from the committed ncu capture taken at this launch size
+        # (profiles/r02_km_traffic.json); null when the capture was made at another launch size
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_km_traffic.json")))
+            if int(tr["images_per_launch"]) == launch_group:
+                traffic, traffic_src = float(tr["dram_bytes_per_launch"]), tr["source"]
+        except Exception:
+            pass
+        roof_km = {"kernel": "km_tile_kernel<8,256,2> (%d launches per %d-image launch group, timed with their km_finalize_kernel)"
+                             % (ITERS, launch_group), "bound": "hbm",
                    "achieved": km_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": km_gbs / hbm_peak,
-                   "traffic": traffic_per_image_pass * min(group, B), "algorithmic_bytes_per_launch": (N * D * 4) * min(group, B),
-                   "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_launches.csv",
+                   "traffic": traffic, "algorithmic_bytes_per_launch": (N * D * 4) * launch_group,
+                   "images_per_launch": launch_group, "traffic_source": traffic_src,
                    "peak_source": peak_src, "ms_per_step": stage["kmeans"]}
-        roof_gb = {"kernel": "gabor_bank_kernel", "bound": "fp32", "achieved": gb_tfs,
-                   "peak": fma_peak.get("ffma_rrr_tflops"), "unit": "TFLOP/s",
-                   "frac": (gb_tfs / fma_peak["ffma_rrr_tflops"]) if fma_peak.get("ffma_rrr_tflops") else None,
+        fp32_peak = fma_peak.get("ffma_rrr_tflops")
+        # FLOPs that still run on the FP32 pipe: the column pass, 12 of the 19 real taps per pixel, channel and scale of
+        # the executed 3.66 GFLOP/image; the row pass runs as bf16 MMAs on the tensor cores
+        col_flop = B * 3.66e9 * (12.0 / 19.0 if uses_tc else 1.0)
+        roof_gb = {"kernel": "gabor_tc_kernel (row pass: tcgen05 bf16x3 MMA, column pass: FFMA2)" if uses_tc else "gabor_bank_kernel",
+                   "bound": "fp32", "achieved": gb_tfs, "peak": fp32_peak, "unit": "TFLOP/s",
+                   "frac": (gb_tfs / fp32_peak) if fp32_peak else None,
+                   "note": "achieved = SURVEY 8(d) count (6.98 GFLOP/image, un-paired complex-separable) / event time; with the row "
+                           "pass on the tensor cores this can exceed the FP32-pipe peak" if uses_tc else
+                           "achieved = SURVEY 8(d) count (6.98 GFLOP/image) / event time",
+                   "fp32_pipe_executed": {"tflops": col_flop / (stage["gabor"] * 1e-3) / 1e12,
+                                          "frac": (col_flop / (stage["gabor"] * 1e-3) / 1e12 / fp32_peak) if fp32_peak else None,
+                                          "what": "FLOPs executed on the FP32 pipe per image: %.2f G" % (col_flop / B / 1e9)},
                    "traffic": None, "peak_source": "measured in this run (benchmarks/fma_peak)",
                    "hbm_gbs": gabor_bytes / (stage["gabor"] * 1e-3) / 1e9, "ms_per_step": stage["gabor"]}
         line = {
@@ -291,7 +315,7 @@ def run_gpu(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: %d-image synthetic BSDS-shaped batch per GPU, 321x481 RGB, "
                                    "bank 4 scales x 6 orientations, k-means k=8 T=20, BSD metrics vs 5 ground truths" % B,
-                       "images_per_step_per_gpu": B, "unique_images": unique, "group": args.group,
+                       "images_per_step_per_gpu": B, "unique_images": unique, "images_per_launch": launch_group,
                        "l2": "inputs + feature tensor (%.1f GB per step) far exceed the 126 MB L2" % (B * N * D * 4 / 1e9)},
             "e2e": {"value": total_imgs / (e2e_ms * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": int(h_img.numel() + h_gt.numel() * 2 + h_idx.numel() * 4),
@@ -301,6 +325,7 @@ def run_gpu(args):
             "roofline": roof_km if dominant == "kmeans" else roof_gb,
             "roofline_other": roof_gb if dominant == "kmeans" else roof_km,
             "stage_ms_per_step": stage,
+            "latency_ms_1img": latency,
             "fma_peak": fma_peak,
             "dataset_scores": {k: float(sums[i] / sums[-1]) for i, k in enumerate(SUM_KEYS)},
         }
@@ -311,10 +336,38 @@ def run_gpu(args):
             line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
                                     "sample": "%d images, one per host thread, %.1f s: C oracle (fp64 separable Gabor + "
                                               "fp32-exact k-means + BSD metrics)" % (n, dt)}
+            if not args.no_ref_metrics:
+                from benchmarks import cpu_baselines
+                line["cpu_baseline"].update(cpu_baselines.measure(threads))
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def one_image_latency(img, gts, reps=20):
+    """BASELINE config 1 through the drop-in surface: one script.py iteration = labels = segmenter(img);
+    metrics(img, labels, gts).set_metrics().  Host arrays in, floats out; median wall-clock ms."""
+    import torch
+    from gabor_color_image_segmentation_b200 import gabor_kmeans_segment, metrics
+    gl = list(gts)
+
+    def once():
+        t0 = time.perf_counter()
+        labels = gabor_kmeans_segment(img, n_clusters=K_CLUSTERS, n_iter=ITERS)
+        t1 = time.perf_counter()
+        m = metrics(img, labels, gl)
+        m.set_metrics()
+        t2 = time.perf_counter()
+        return (t1 - t0) * 1e3, (t2 - t1) * 1e3
+    for _ in range(3):
+        once()
+    torch.cuda.synchronize()
+    t = np.array([once() for _ in range(reps)])
+    return {"segment": float(np.median(t[:, 0])), "metrics": float(np.median(t[:, 1])),
+            "total": float(np.median(t.sum(1))), "reps": reps,
+            "what": "gabor_kmeans_segment(img) + metrics(img, labels, 5 ground truths).set_metrics(), one 321x481 image, "
+                    "host arrays in and out, median wall clock"}
 
 
 def measure_fma_peak():
@@ -333,7 +386,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=200, help="images per step per GPU")
-    ap.add_argument("--unique", type=int, default=48, help="distinct synthetic images generated per rank (cycled)")
+    ap.add_argument("--unique", type=int, default=200, help="distinct synthetic images generated per rank (cycled if fewer than --images)")
+    ap.add_argument("--no-ref-metrics", action="store_true", help="skip timing the reference's own metrics.py and the strong CPU baseline")
     ap.add_argument("--group", type=int, default=0, help="images per launch group (0 = library default, 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

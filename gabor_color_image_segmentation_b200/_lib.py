@@ -68,6 +68,8 @@ SIGNATURES = {
     "gcis_plan_destroy": (None, [_vp]),
     "gcis_plan_feature_dim": (_i32, [_vp]),
     "gcis_plan_workspace_bytes": (_i64, [_vp]),
+    "gcis_plan_launch_group": (_i32, [_vp, _i32]),
+    "gcis_plan_uses_tensor_cores": (_i32, [_vp]),
     "gcis_gabor_features": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "gcis_kmeans": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "gcis_segment_device": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp]),

@@ -189,6 +189,45 @@ int pipeline_range(gcis_plan *p, int lane, const uint8_t *d_img, const uint16_t 
 
 }  // namespace
 
+// Grow-only device scratch of the calling thread for the host-buffer entry points below: one allocation that is
+// reused by later calls (a drop-in `metrics(...)` call used to pay 11 cudaMalloc + 11 cudaFree, each of which
+// synchronises the device).  Freed when the thread exits.
+namespace {
+struct ScratchArena {
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+    int device = -1;
+    ~ScratchArena() { if (base) cudaFree(base); }
+    int reserve(size_t bytes)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (base && (dev != device || bytes > cap)) { cudaFree(base); base = nullptr; cap = 0; }
+        if (!base) {
+            const size_t want = std::max<size_t>(bytes, 1 << 20);
+            cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&base), want);
+            if (e != cudaSuccess) {
+                base = nullptr;
+                return set_error(e == cudaErrorMemoryAllocation ? GCIS_E_NOMEM : GCIS_E_CUDA, "cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e));
+            }
+            cap = want; device = dev;
+        }
+        used = 0;
+        return GCIS_OK;
+    }
+    template <typename T>
+    T *take(size_t n)
+    {
+        used = (used + 255) & ~(size_t)255;
+        T *p = reinterpret_cast<T *>(base + used);
+        used += std::max<size_t>(n, 1) * sizeof(T);
+        return p;
+    }
+};
+thread_local ScratchArena g_arena;
+inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
+}  // namespace
+
 extern "C" {
 
 int32_t gcis_version(void) { return GCIS_VERSION; }
@@ -359,6 +398,8 @@ void gcis_plan_destroy(gcis_plan *p)
 }
 
 int32_t gcis_plan_feature_dim(const gcis_plan *p) { return p ? p->D : set_error(GCIS_E_INVALID, "null plan"); }
+int32_t gcis_plan_launch_group(const gcis_plan *p, int32_t B) { return p ? balanced_group(p, B) : set_error(GCIS_E_INVALID, "null plan"); }
+int32_t gcis_plan_uses_tensor_cores(const gcis_plan *p) { return p ? (p->gtc != nullptr) : set_error(GCIS_E_INVALID, "null plan"); }
 int64_t gcis_plan_workspace_bytes(const gcis_plan *p) { return p ? (int64_t)p->bytes : 0; }
 
 int32_t gcis_plan_set_profiling(gcis_plan *p, int32_t on)
@@ -449,48 +490,43 @@ int32_t gcis_label_metrics_host(const int32_t *h_lb, const uint16_t *h_gt, const
 {
     if (B < 1 || H < 1 || W < 1 || G < 0 || n_seg_cap < 1 || n_lab_cap < 1)
         return set_error(GCIS_E_INVALID, "label_metrics_host: bad shape");
-    const size_t N = (size_t)H * W, Gs = G;
-    size_t tot = 0;
-    int32_t *d_lb = nullptr, *d_n_gt = nullptr, *d_area = nullptr, *d_perim = nullptr, *d_hist = nullptr, *d_n_seg = nullptr,
-            *d_n_lab = nullptr, *d_status = nullptr;
-    uint16_t *d_gt = nullptr;
-    int64_t *d_bd = nullptr, *d_gc = nullptr;
+    const size_t N = (size_t)H * W, Gs = std::max(G, 1), Bs = B;
+    const size_t n_hist = Bs * Gs * n_seg_cap * n_lab_cap;
+    const size_t total = pad256(4 * Bs * N) + pad256(2 * Bs * Gs * N) + pad256(4 * Bs) + 2 * pad256(4 * Bs * n_seg_cap) +
+                         pad256(4 * n_hist) + pad256(4 * Bs) + pad256(4 * Bs * Gs) + pad256(4 * Bs) + pad256(8 * Bs) +
+                         pad256(8 * Bs * Gs * GCIS_GT_SLOTS) + 4096;
+    TRY(g_arena.reserve(total));
+    int32_t *d_lb = g_arena.take<int32_t>(Bs * N);
+    uint16_t *d_gt = g_arena.take<uint16_t>(Bs * Gs * N);
+    int32_t *d_n_gt = g_arena.take<int32_t>(Bs), *d_area = g_arena.take<int32_t>(Bs * n_seg_cap), *d_perim = g_arena.take<int32_t>(Bs * n_seg_cap);
+    int32_t *d_hist = g_arena.take<int32_t>(n_hist), *d_n_seg = g_arena.take<int32_t>(Bs), *d_n_lab = g_arena.take<int32_t>(Bs * Gs);
+    int32_t *d_status = g_arena.take<int32_t>(Bs);
+    int64_t *d_bd = g_arena.take<int64_t>(Bs), *d_gc = g_arena.take<int64_t>(Bs * Gs * GCIS_GT_SLOTS);
     int rc = GCIS_OK;
-    auto cleanup = [&]() {
-        cudaFree(d_lb); cudaFree(d_n_gt); cudaFree(d_area); cudaFree(d_perim); cudaFree(d_hist); cudaFree(d_n_seg);
-        cudaFree(d_n_lab); cudaFree(d_status); cudaFree(d_gt); cudaFree(d_bd); cudaFree(d_gc);
-    };
-#define HA(ptr, n)                                   \
-    if (!rc) rc = dev_alloc(&(ptr), (n), &tot);
-    HA(d_lb, B * N) HA(d_gt, B * Gs * N) HA(d_n_gt, B) HA(d_area, (size_t)B * n_seg_cap) HA(d_perim, (size_t)B * n_seg_cap)
-    HA(d_hist, (size_t)B * Gs * n_seg_cap * n_lab_cap) HA(d_n_seg, B) HA(d_n_lab, B * Gs) HA(d_status, B) HA(d_bd, B)
-    HA(d_gc, B * Gs * GCIS_GT_SLOTS)
-#undef HA
-    if (rc) { cleanup(); return rc; }
+    // pageable host memory: the copies are staged by the driver; everything is ordered on the legacy default stream
     auto cp = [&](void *dst, const void *src, size_t n, cudaMemcpyKind kind) {
         if (rc || n == 0) return;
-        cudaError_t e = cudaMemcpy(dst, src, n, kind);
+        cudaError_t e = cudaMemcpyAsync(dst, src, n, kind, nullptr);
         if (e != cudaSuccess) rc = set_error(GCIS_E_CUDA, "label_metrics_host: cudaMemcpy -> %s", cudaGetErrorString(e));
     };
-    cp(d_lb, h_lb, sizeof(int32_t) * B * N, cudaMemcpyHostToDevice);
-    cp(d_gt, h_gt, sizeof(uint16_t) * B * Gs * N, cudaMemcpyHostToDevice);
-    if (h_n_gt) cp(d_n_gt, h_n_gt, sizeof(int32_t) * B, cudaMemcpyHostToDevice);
+    cp(d_lb, h_lb, sizeof(int32_t) * Bs * N, cudaMemcpyHostToDevice);
+    if (G > 0) cp(d_gt, h_gt, sizeof(uint16_t) * Bs * Gs * N, cudaMemcpyHostToDevice);
+    if (h_n_gt) cp(d_n_gt, h_n_gt, sizeof(int32_t) * Bs, cudaMemcpyHostToDevice);
     if (!rc)
         rc = label_metrics_launch(d_lb, d_gt, h_n_gt ? d_n_gt : nullptr, B, H, W, G, n_seg_cap, n_lab_cap, dil_recall, d_bd,
                                   d_gc, d_area, d_perim, d_hist, d_n_seg, d_n_lab, d_status, nullptr);
+    cp(h_bd_count, d_bd, sizeof(int64_t) * Bs, cudaMemcpyDeviceToHost);
+    cp(h_gt_counts, d_gc, sizeof(int64_t) * Bs * Gs * GCIS_GT_SLOTS, cudaMemcpyDeviceToHost);
+    cp(h_area, d_area, sizeof(int32_t) * Bs * n_seg_cap, cudaMemcpyDeviceToHost);
+    cp(h_perim, d_perim, sizeof(int32_t) * Bs * n_seg_cap, cudaMemcpyDeviceToHost);
+    if (h_hist) cp(h_hist, d_hist, sizeof(int32_t) * n_hist, cudaMemcpyDeviceToHost);
+    cp(h_n_seg, d_n_seg, sizeof(int32_t) * Bs, cudaMemcpyDeviceToHost);
+    cp(h_n_lab, d_n_lab, sizeof(int32_t) * Bs * Gs, cudaMemcpyDeviceToHost);
+    cp(h_status, d_status, sizeof(int32_t) * Bs, cudaMemcpyDeviceToHost);
     if (!rc) {
-        cudaError_t e = cudaDeviceSynchronize();
+        cudaError_t e = cudaStreamSynchronize(nullptr);
         if (e != cudaSuccess) rc = set_error(GCIS_E_CUDA, "label_metrics_host: kernel -> %s", cudaGetErrorString(e));
     }
-    cp(h_bd_count, d_bd, sizeof(int64_t) * B, cudaMemcpyDeviceToHost);
-    cp(h_gt_counts, d_gc, sizeof(int64_t) * B * Gs * GCIS_GT_SLOTS, cudaMemcpyDeviceToHost);
-    cp(h_area, d_area, sizeof(int32_t) * (size_t)B * n_seg_cap, cudaMemcpyDeviceToHost);
-    cp(h_perim, d_perim, sizeof(int32_t) * (size_t)B * n_seg_cap, cudaMemcpyDeviceToHost);
-    if (h_hist) cp(h_hist, d_hist, sizeof(int32_t) * (size_t)B * Gs * n_seg_cap * n_lab_cap, cudaMemcpyDeviceToHost);
-    cp(h_n_seg, d_n_seg, sizeof(int32_t) * B, cudaMemcpyDeviceToHost);
-    cp(h_n_lab, d_n_lab, sizeof(int32_t) * B * Gs, cudaMemcpyDeviceToHost);
-    cp(h_status, d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost);
-    cleanup();
     if (!rc)
         for (int b = 0; b < B; ++b)
             if (h_status[b]) return set_error(GCIS_E_LABEL, "label_metrics: image %d has status %d (negative label or label >= capacity)", b, h_status[b]);
@@ -501,18 +537,14 @@ int32_t gcis_find_boundaries_host(const int32_t *h_x, int32_t B, int32_t H, int3
 {
     if (!h_x || !h_out || B < 1 || H < 1 || W < 1) return set_error(GCIS_E_INVALID, "find_boundaries: bad argument");
     const size_t n = (size_t)B * H * W;
-    int32_t *d_x = nullptr;
-    uint8_t *d_o = nullptr;
-    size_t tot = 0;
-    int rc = dev_alloc(&d_x, n, &tot);
-    if (!rc) rc = dev_alloc(&d_o, n, &tot);
-    if (!rc && cudaMemcpy(d_x, h_x, n * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess)
-        rc = set_error(GCIS_E_CUDA, "find_boundaries: H2D copy failed");
-    if (!rc) rc = find_boundaries_launch(d_x, d_o, B, H, W, nullptr);
-    if (!rc && cudaMemcpy(h_out, d_o, n, cudaMemcpyDeviceToHost) != cudaSuccess)
-        rc = set_error(GCIS_E_CUDA, "find_boundaries: %s", cudaGetErrorString(cudaGetLastError()));
-    cudaFree(d_x); cudaFree(d_o);
-    return rc;
+    TRY(g_arena.reserve(pad256(n * 4) + pad256(n) + 1024));
+    int32_t *d_x = g_arena.take<int32_t>(n);
+    uint8_t *d_o = g_arena.take<uint8_t>(n);
+    GCIS_CUDA_TRY(cudaMemcpyAsync(d_x, h_x, n * sizeof(int32_t), cudaMemcpyHostToDevice, nullptr));
+    TRY(find_boundaries_launch(d_x, d_o, B, H, W, nullptr));
+    GCIS_CUDA_TRY(cudaMemcpyAsync(h_out, d_o, n, cudaMemcpyDeviceToHost, nullptr));
+    GCIS_CUDA_TRY(cudaStreamSynchronize(nullptr));
+    return GCIS_OK;
 }
 
 int32_t gcis_pipeline_device(gcis_plan *p, const uint8_t *d_img, const uint16_t *d_gt, const int32_t *d_n_gt,

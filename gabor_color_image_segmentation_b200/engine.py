@@ -102,6 +102,14 @@ class Plan:
     def workspace_bytes(self) -> int:
         return int(self.lib.gcis_plan_workspace_bytes(self._h))
 
+    def launch_group(self, B: int) -> int:
+        """Images per kernel launch for a batch of B images."""
+        return _lib.check(self.lib.gcis_plan_launch_group(self._h, int(B)))
+
+    @property
+    def uses_tensor_cores(self) -> bool:
+        return bool(_lib.check(self.lib.gcis_plan_uses_tensor_cores(self._h)))
+
     @staticmethod
     def _stream():
         return C.c_void_p(_torch().cuda.current_stream().cuda_stream)

@@ -123,6 +123,11 @@ GCIS_API int32_t gcis_plan_create(const gcis_config *cfg, gcis_plan **out);
 GCIS_API void gcis_plan_destroy(gcis_plan *plan);
 GCIS_API int32_t gcis_plan_feature_dim(const gcis_plan *plan); /* D = 3 * n_scales * n_orient */
 GCIS_API int64_t gcis_plan_workspace_bytes(const gcis_plan *plan);
+/* images per kernel launch when a batch of B images runs through the plan (the batch is cut into equal groups) */
+GCIS_API int32_t gcis_plan_launch_group(const gcis_plan *plan, int32_t B);
+/* 1 when the filter bank's row pass runs on the tcgen05 tensor cores (rgb planes, exact in bf16), 0 when both
+ * passes run on the FP32 pipe (opponent / Lab planes, or GCIS_GABOR_TC=0) */
+GCIS_API int32_t gcis_plan_uses_tensor_cores(const gcis_plan *plan);
 
 /* ---- segmenter slot (script.py:30), device pointers ----
  * d_img      [B][H][W][3] uint8 (interleaved RGB, as skimage.io.imread returns it)

@@ -175,6 +175,7 @@ def run_gpu(args):
     # every rank gets its own images (weak scaling); generate `unique` of them and cycle.
     # Host-side generation forks workers, so it runs before CUDA/NCCL are initialised.
     unique = min(B, args.unique)
+    pinned = pin_to_local_cores(local, world)
     imgs_u, gts_u = make_data(unique, start=rank * 100_000, workers=max(1, min(16, (os.cpu_count() or 1) // max(world, 1))))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -322,6 +323,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(B * (8 + G * 8 * 8 + 2 * K_CLUSTERS * 4 + G * 4 + 4))},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "host_pinning": pinned,
             "roofline": roof_km if dominant == "kmeans" else roof_gb,
             "roofline_other": roof_gb if dominant == "kmeans" else roof_km,
             "stage_ms_per_step": stage,
@@ -343,6 +345,176 @@ def run_gpu(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def pin_to_local_cores(local, world_local):
+    """Keep this rank's threads (and the pinned staging buffers it first-touches) on the host cores nearest to its GPU:
+    the GPU's NUMA node when the box has several, otherwise an even slice of the cores, so that N ranks do not
+    migrate over one another's caches.  Returns a description for the bench line."""
+    try:
+        import torch
+        cpus = sorted(os.sched_getaffinity(0))
+        pci = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        node = -1
+        if pci is not None:
+            import glob
+            for path in glob.glob("/sys/bus/pci/devices/*:%02x:*/numa_node" % pci):
+                node = int(open(path).read().strip())
+                break
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()] \
+            if os.path.isdir("/sys/devices/system/node") else []
+        if node >= 0 and len(nodes) > 1:
+            txt = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+            want = set()
+            for part in txt.split(","):
+                a, _, b = part.partition("-")
+                want.update(range(int(a), int(b or a) + 1))
+            mine = [c for c in cpus if c in want] or cpus
+            how = "numa node %d" % node
+        else:
+            per = max(1, len(cpus) // max(world_local, 1))
+            mine = cpus[local * per:(local + 1) * per] or cpus
+            how = "core slice (single NUMA node)"
+        os.sched_setaffinity(0, mine)
+        return {"cores": len(mine), "how": how}
+    except Exception as e:  # noqa: BLE001
+        return {"cores": None, "how": "not pinned: %s" % e}
+
+
+def run_gpu_strong(args):
+    """BASELINE config 5: ONE fixed batch of --total-images synthetic images sharded over the ranks
+    (image i -> rank i mod N, pipeline.shard_indices), NCCL sum of the metric sums every step and one all-gather
+    of the integer records; the gathered table (and therefore every score finished from it in global image
+    order) must be identical for 1/2/4/8 GPUs: the line carries its sha256.
+    Image i of the batch is synthetic image (i mod --unique) clustered from its own initial centroids (seeded by
+    the global index i), so all --total-images results differ while only --unique images are generated."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from gabor_color_image_segmentation_b200 import Plan, _lib
+    from gabor_color_image_segmentation_b200.metrics import finish_batch
+    from gabor_color_image_segmentation_b200 import pipeline as pl
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    total, U, B = args.total_images, min(args.unique, args.total_images), args.images
+    if U % world:
+        raise SystemExit("--unique must be a multiple of the number of GPUs in strong-scaling mode")
+    mine = pl.shard_indices(total, rank, world)                       # global indices of this rank
+    uniq = np.arange(rank, U, world)                                  # synthetic images this rank ever sees
+    pinned = pin_to_local_cores(local, world)
+    imgs_u, gts_u = make_data_indices(uniq, workers=max(1, min(16, (os.cpu_count() or 1) // max(world, 1))))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pos = {int(u): n for n, u in enumerate(uniq)}
+    sel = np.array([pos[int(i) % U] for i in mine], np.int64)         # this rank's images as rows of imgs_u
+    chunks = [np.arange(a, min(a + B, len(mine))) for a in range(0, len(mine), B)]
+    plan = Plan(H, W, max_batch=B, k=K_CLUSTERS, iters=ITERS, max_gt=G, n_lab_cap=64, group=args.group)
+    idx_all = pl.init_indices_for(mine, H * W, K_CLUSTERS)
+    # inputs of every step, host (pinned) and device.  Steps whose images coincide (the batch cycles through the
+    # rank's --unique / N synthetic images) share one payload; only the initial-centroid indices differ per step.
+    payload_h, payload_d, h_chunks, d_in = {}, {}, [], []
+    for ch in chunks:
+        key = sel[ch].tobytes()
+        if key not in payload_h:
+            payload_h[key] = (torch.from_numpy(imgs_u[sel[ch]]).pin_memory(), torch.from_numpy(gts_u[sel[ch]].view(np.int16)).pin_memory())
+            payload_d[key] = tuple(t.to(dev) for t in payload_h[key])
+        ix = torch.from_numpy(idx_all[ch]).pin_memory()
+        h_chunks.append(payload_h[key] + (ix,))
+        d_in.append(payload_d[key] + (ix.to(dev),))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(host):
+        recs, sums = [], np.zeros(7)
+        for n, ch in enumerate(chunks):
+            if host:
+                im, gt, ix = h_chunks[n]
+                c = plan.pipeline_host(im, gt, ix, len(ch))
+            else:
+                plan.pipeline_device(*d_in[n])
+                c = plan.fetch()
+            m = finish_batch(c)
+            sums = sums + pl.reduce_sums(np.array([m[k].sum() for k in pl.SUM_KEYS] + [float(len(ch))]), dev)
+            recs.append(pl.records_to_array(c))
+        table = pl.gather_records(np.concatenate(recs) if recs else np.zeros((0, 3 + 2 * K_CLUSTERS + G * 8), np.int64),
+                                  mine, total, dev)
+        return table, sums
+
+    plan.pipeline_device(*d_in[0]); plan.fetch()                      # warm-up (3 passes)
+    plan.pipeline_device(*d_in[0]); plan.fetch()
+    plan.pipeline_host(*h_chunks[0], len(chunks[0]))
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    table, sums = run(host=False)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.summary()
+    barrier()
+    t0 = time.perf_counter()
+    table_h, sums_h = run(host=True)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+    assert np.array_equal(table, table_h), "device-resident and host-buffer passes disagree"
+    if rank == 0:
+        back = pl.array_to_records(table, H, W, K_CLUSTERS, G)
+        m = finish_batch(back)                                        # floats finished in GLOBAL image order
+        scores = {k: float(np.sum(m[k]) / total) for k in pl.SUM_KEYS}
+        h2d = sum(int(a.numel() + b.numel() * 2 + c.numel() * 4) for a, b, c in h_chunks)
+        line = {"metric": METRIC, "value": total / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": len(chunks),
+                "warmup": 3, "ms_per_step": ms / max(len(chunks), 1), "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[4]: one fixed %d-image synthetic batch (321x481 RGB, bank 4x6, k=8 T=20, 5 ground "
+                                       "truths) sharded over the GPUs, image i -> rank i mod N; NCCL all-reduce of the metric sums "
+                                       "per %d-image step and one all-gather of the integer records" % (total, B),
+                           "total_images": total, "unique_images": U, "images_per_step_per_gpu": B,
+                           "images_per_launch": plan.launch_group(B),
+                           "l2": "inputs + feature tensor far exceed the 126 MB L2"},
+                "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d // max(len(chunks), 1),
+                        "d2h_bytes_per_step": int(B * (8 + G * 8 * 8 + 2 * K_CLUSTERS * 4 + G * 4 + 4))},
+                "gpu_launches": int(launches), "clocks": clocks, "host_pinning": pinned,
+                "records_table_sha256": hashlib.sha256(np.ascontiguousarray(table).tobytes()).hexdigest(),
+                "records_table_shape": list(table.shape),
+                "dataset_scores": scores,
+                "dataset_scores_reduced": {k: float(sums[i] / sums[-1]) for i, k in enumerate(pl.SUM_KEYS)}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def make_data_indices(indices, workers=None):
+    """Synthetic images + ground truths for explicit global indices."""
+    from concurrent.futures import ProcessPoolExecutor
+    from gabor_color_image_segmentation_b200.synth import synth_image, synth_ground_truths
+    idx = [int(i) for i in indices]
+    workers = workers or min(os.cpu_count() or 1, 16)
+    if len(idx) <= 4 or workers <= 1:
+        imgs = [synth_image(i, H, W) for i in idx]
+        gts = [synth_ground_truths(i, H, W, G) for i in idx]
+    else:
+        with ProcessPoolExecutor(workers) as ex:
+            imgs = list(ex.map(synth_image, idx, chunksize=4))
+            gts = list(ex.map(synth_ground_truths, idx, chunksize=4))
+    return np.stack(imgs), np.stack(gts)
 
 
 def one_image_latency(img, gts, reps=20):
@@ -390,9 +562,15 @@ def main():
     ap.add_argument("--no-ref-metrics", action="store_true", help="skip timing the reference's own metrics.py and the strong CPU baseline")
     ap.add_argument("--group", type=int, default=0, help="images per launch group (0 = library default, 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --images per GPU per step (default, BASELINE configs[1]); strong: one fixed --total-images batch "
+                         "sharded over the GPUs (BASELINE configs[4])")
+    ap.add_argument("--total-images", type=int, default=10000, help="size of the fixed batch in strong-scaling mode")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.scaling == "strong":
+        return run_gpu_strong(args)
     return run_gpu(args)
 
 

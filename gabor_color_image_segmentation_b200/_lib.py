@@ -9,7 +9,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GCIS_LIB") or os.path.join(_PKG, "libgcis.so")
 CSRC = os.path.join(_PKG, "csrc")
-SOURCES = ["plan.cu", "gabor.cu", "gabor_tc.cu", "kmeans.cu", "label_metrics.cu"]
+SOURCES = ["plan.cu", "gabor.cu", "gabor_tc.cu", "features.cu", "kmeans.cu", "label_metrics.cu"]
 
 GT_SLOTS = 8
 COLOUR = {"rgb": 0, "opponent": 1, "lab": 2}
@@ -29,6 +29,7 @@ class GcisConfig(C.Structure):
         ("bandwidth", C.c_double), ("n_stds", C.c_double),
         ("feature", C.c_int32), ("k", C.c_int32), ("iters", C.c_int32), ("fix_shift", C.c_int32),
         ("max_gt", C.c_int32), ("n_lab_cap", C.c_int32), ("dil_recall", C.c_int32), ("group", C.c_int32),
+        ("normalise", C.c_int32), ("smooth", C.c_double),
     ]
 
 
@@ -72,6 +73,7 @@ SIGNATURES = {
     "gcis_plan_uses_tensor_cores": (_i32, [_vp]),
     "gcis_gabor_features": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "gcis_kmeans": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "gcis_feature_affine": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "gcis_segment_device": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "gcis_label_metrics_device": (_i32, [_vp, _vp, _vp] + [_i32] * 7 + [_vp] * 8 + [_vp]),
     "gcis_label_metrics_host": (_i32, [_vp, _vp, _vp] + [_i32] * 7 + [_vp] * 8),

@@ -325,10 +325,12 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
         float *f0 = featb + (size_t)(d0 + job.out0) * P.feat_plane_stride;
         float *f1 = job.out1 >= 0 ? featb + (size_t)(d0 + job.out1) * P.feat_plane_stride : nullptr;
         const bool cx = job.row_im >= 0, ct = job.col_im >= 0;
-        if (cx && ct) col_pass<true, true>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1);
-        else if (cx) col_pass<true, false>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1);
-        else if (ct) col_pass<false, true>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1);
-        else col_pass<false, false>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1);
+        long long *st0 = P.stats ? P.stats + ((size_t)b * D + d0 + job.out0) * GB_STAT_SLOTS : nullptr;
+        long long *st1 = P.stats && job.out1 >= 0 ? P.stats + ((size_t)b * D + d0 + job.out1) * GB_STAT_SLOTS : nullptr;
+        if (cx && ct) col_pass<true, true>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1, GB_WARPS, st0, st1);
+        else if (cx) col_pass<true, false>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1, GB_WARPS, st0, st1);
+        else if (ct) col_pass<false, true>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1, GB_WARPS, st0, st1);
+        else col_pass<false, false>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1, GB_WARPS, st0, st1);
         GB_TR_ADD(3);
     }
 #ifdef GB_TRACE
@@ -434,9 +436,10 @@ GaborLaunchPlan *gabor_plan_new(const GaborBankHost &bank, int H, int W, int C, 
 void gabor_plan_delete(GaborLaunchPlan *lp) { delete lp; }
 
 int gabor_launch(GaborLaunchPlan &lp, const float *d_planes, float *d_feat, const float *d_taps,
-                 const GaborScale *d_scales, int B, int feat_plane_stride, cudaStream_t st)
+                 const GaborScale *d_scales, int B, int feat_plane_stride, cudaStream_t st, long long *d_stats, float stat_scale)
 {
     GaborParams &p = lp.p;
+    p.stats = d_stats; p.stat_scale = stat_scale;
     p.planes = d_planes; p.feat = d_feat; p.taps = d_taps; p.scales = d_scales; p.B = B;
     p.feat_plane_stride = feat_plane_stride;
     int acc = 0;

@@ -40,6 +40,10 @@ struct GaborParams {
     int istr;                    // chunk row stride: 32 n + 4 floats (aligned, conflict-free 128-bit row loads)
     int tap_slot;                // floats reserved per staged filter (complex, interleaved) in shared memory
     int rowtab_cap;
+    // per-plane moments for the optional normalisation, accumulated in the epilogue:
+    // [B][D]{sum q, sum lo32(r^2), sum hi32(r^2)} with q = rint(x 2^fix_shift), r = rint(x 2^16) (GB_STAT_SLOTS = 3)
+    long long *stats;            // null = not requested
+    float stat_scale;            // 2^fix_shift
 };
 
 typedef unsigned long long u64;
@@ -309,12 +313,14 @@ __device__ __forceinline__ float fast_sqrt(float x)
 // Column pass: lane = column of the strip, warp = blocks of GB_RC output rows.
 template <bool CX, bool CT>
 __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, const int *rowtab, const float *w0,
-                                         int nblk, int y0, int th, int x0, float *feat0, float *feat1, int nwarps = GB_WARPS)
+                                         int nblk, int y0, int th, int x0, float *feat0, float *feat1, int nwarps = GB_WARPS,
+                                         long long *st0 = nullptr, long long *st1 = nullptr)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nrb = (th + GB_RC - 1) / GB_RC;
     const bool col_ok = x0 + lane < P.W;
     const u64 *Tl = reinterpret_cast<const u64 *>(T) + lane;
+    long long m1[2] = {0, 0}, m2[2] = {0, 0}, m3[2] = {0, 0};   // exact integer moments of what this thread writes (normalisation)
     for (int rb = warp; rb < nrb; rb += nwarps) {
         u64 Pv[GB_RC], Qv[GB_RC];
         float Sv[GB_RC];
@@ -344,13 +350,25 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
                 const float re0 = A - Bv, im0 = Cv + Dv;
                 const float e0 = fmaf(re0, re0, im0 * im0);
                 const size_t o = (size_t)(y0 + r) * P.W + x0 + lane;
-                feat0[o] = P.feature == GCIS_FEATURE_MAGNITUDE ? fast_sqrt(e0) : e0;
+                const float v0 = P.feature == GCIS_FEATURE_MAGNITUDE ? fast_sqrt(e0) : e0;
+                feat0[o] = v0;
+                if (st0) stat_add(v0, P.stat_scale, m1[0], m2[0], m3[0]);
                 if (feat1) {
                     const float re1 = A + Bv, im1 = Dv - Cv;
                     const float e1 = fmaf(re1, re1, im1 * im1);
-                    feat1[o] = P.feature == GCIS_FEATURE_MAGNITUDE ? fast_sqrt(e1) : e1;
+                    const float v1 = P.feature == GCIS_FEATURE_MAGNITUDE ? fast_sqrt(e1) : e1;
+                    feat1[o] = v1;
+                    if (st1) stat_add(v1, P.stat_scale, m1[1], m2[1], m3[1]);
                 }
             }
+        }
+    }
+    if (st0) {   // warp-shuffle reduction, then one atomic per warp, plane and moment (integers: order-independent)
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+            long long *dst = pl ? st1 : st0;
+            if (!dst) continue;
+            stat_flush(dst, m1[pl], m2[pl], m3[pl], lane);
         }
     }
 }

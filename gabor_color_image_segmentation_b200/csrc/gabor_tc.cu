@@ -339,10 +339,12 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
                 float *f1 = job.out1 >= 0 ? featb + (size_t)(d0 + job.out1) * P.feat_plane_stride : nullptr;
                 const int *rt = rowtab + (w.hmax - h);
                 const bool cx = job.row_im >= 0, ct = job.col_im >= 0;
-                if (cx && ct) col_pass<true, true>(P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW);
-                else if (cx) col_pass<true, false>(P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW);
-                else if (ct) col_pass<false, true>(P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW);
-                else col_pass<false, false>(P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW);
+                long long *st0 = P.stats ? P.stats + ((size_t)w.b * D + d0 + job.out0) * GB_STAT_SLOTS : nullptr;
+                long long *st1 = P.stats && job.out1 >= 0 ? P.stats + ((size_t)w.b * D + d0 + job.out1) * GB_STAT_SLOTS : nullptr;
+                if (cx && ct) col_pass<true, true>(P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW, st0, st1);
+                else if (cx) col_pass<true, false>(P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW, st0, st1);
+                else if (ct) col_pass<false, true>(P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW, st0, st1);
+                else col_pass<false, false>(P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW, st0, st1);
                 TC_TR_ADD(3);
                 named_bar_sync(1, TC_COLT);                                          // T may be overwritten
                 TC_TR_ADD(5);
@@ -539,9 +541,10 @@ int colour_planes16_launch(const uint8_t *d_img, void *d_planes16, int B, int H,
 }
 
 int gabor_tc_launch(GaborTcPlan &tp, const void *d_planes16, float *d_feat, const float *d_taps, const GaborScale *d_scales,
-                    int B, int feat_plane_stride, cudaStream_t st)
+                    int B, int feat_plane_stride, cudaStream_t st, long long *d_stats, float stat_scale)
 {
     GaborParams &p = tp.q.g;
+    p.stats = d_stats; p.stat_scale = stat_scale;
     p.planes = nullptr; p.feat = d_feat; p.taps = d_taps; p.scales = d_scales; p.B = B;
     p.feat_plane_stride = feat_plane_stride;
     tp.q.plane_rows = B * p.C * p.H;

@@ -8,6 +8,11 @@
 //   centroid sums are exact int64 sums of q = rint(x * 2^fix_shift) -> the result does not
 //   depend on the grid, the tile order or the number of GPUs
 //   c_jd <- (float)((double)sum_jd / ((double)count_j * 2^fix_shift)); empty clusters keep c_jd
+// With per-feature normalisation (z_d = a_d x_d + b_d, `affine` = [B][D]{a, b}) the clustering runs on z
+// without ever materialising it - no extra HBM traffic: the affine map is folded into the score table,
+//   c_jd (a centroid in z space) <- (float)((double)a_d * (double)cx_jd + (double)b_d),  cx = the x-space mean above,
+//   m'_jd = a_d * (-2 c_jd) (fp32);  cn'_j = (float) sum_d [ (double)c_jd^2 + (double)b_d * (double)(-2 c_jd) ]  (d ascending),
+//   score_j(x) = the same fp32 FMA chain over the RAW features with m' and cn'.
 //
 // Layout: feat [B][D][plane_stride] planar fp32 (a warp load is 512 contiguous bytes of one
 // feature plane); centroids [B][k][D]; per-image score table prep = {m [D][K], cn [K]};
@@ -77,6 +82,7 @@ struct KmParams {
     int D, N, k, chunks, first;
     float fix_scale;
     int pass;
+    const float *affine;    // [B][D][2] {a_d, b_d} of the per-feature normalisation, or null
 };
 
 #ifdef KM_TRACE   // timing experiment only: per-CTA phase timestamps of the first CTAs of each pass
@@ -101,11 +107,14 @@ __device__ __forceinline__ long long km_gtime()
 #endif
 
 // Score table of one image from its centroids (all threads of the CTA; cent must be visible).
-__device__ __forceinline__ void km_write_prep(const float *cent, float *prep, int D, int k, int K, int tid, int nthr)
+__device__ __forceinline__ void km_write_prep(const float *cent, float *prep, int D, int k, int K, int tid, int nthr,
+                                              const float *affine = nullptr)
 {
     for (int i = tid; i < D * K; i += nthr) {
         const int d = i / K, j = i - d * K;
-        prep[i] = j < k ? -2.0f * cent[j * D + d] : 0.f;
+        float m = j < k ? -2.0f * cent[j * D + d] : 0.f;
+        if (affine) m = __fmul_rn(affine[2 * d], m);
+        prep[i] = m;
     }
     if (tid < K) {
         const int j = tid;
@@ -115,6 +124,7 @@ __device__ __forceinline__ void km_write_prep(const float *cent, float *prep, in
             for (int d = 0; d < D; ++d) {
                 const double c = (double)cent[j * D + d];
                 acc = __dadd_rn(acc, __dmul_rn(c, c));
+                if (affine) acc = __dadd_rn(acc, __dmul_rn((double)affine[2 * d + 1], __dmul_rn(-2.0, c)));
             }
             cn = (float)acc;
         }
@@ -122,23 +132,31 @@ __device__ __forceinline__ void km_write_prep(const float *cent, float *prep, in
     }
 }
 
+// centroid in the clustered space from the x-space value (identity without normalisation)
+__device__ __forceinline__ float km_affine(const float *affine, int d, float cx)
+{
+    if (!affine) return cx;
+    return __double2float_rn(__fma_rn((double)affine[2 * d], (double)cx, (double)affine[2 * d + 1]));
+}
+
 __global__ void km_init_kernel(const float *__restrict__ feat, size_t img_stride, int plane_stride,
                                const int32_t *__restrict__ init_idx, float *cent, float *prep, long long *sums,
-                               int *counts, int *done, int D, int N, int k, int K)
+                               int *counts, int *done, int D, int N, int k, int K, const float *affine_all)
 {
     const int b = blockIdx.x;
     float *c = cent + (size_t)b * k * D;
+    const float *affine = affine_all ? affine_all + (size_t)b * D * 2 : nullptr;
     for (int i = threadIdx.x; i < k * D; i += blockDim.x) {
         const int j = i / D, d = i - j * D;
         int p = init_idx[b * k + j];
         p = min(max(p, 0), N - 1);
-        c[i] = feat[(size_t)b * img_stride + (size_t)d * plane_stride + p];
+        c[i] = km_affine(affine, d, feat[(size_t)b * img_stride + (size_t)d * plane_stride + p]);
         sums[(size_t)b * k * D + i] = 0;
     }
     for (int i = threadIdx.x; i < k; i += blockDim.x) counts[b * k + i] = 0;
     if (threadIdx.x == 0) done[b] = 0;
     __syncthreads();
-    km_write_prep(c, prep + (size_t)b * (D * K + K), D, k, K, threadIdx.x, blockDim.x);
+    km_write_prep(c, prep + (size_t)b * (D * K + K), D, k, K, threadIdx.x, blockDim.x, affine);
 }
 
 // acc.{lo,hi} = a.{lo,hi} * b + acc.{lo,hi}, each lane one IEEE fp32 FMA (round to nearest even)
@@ -207,6 +225,7 @@ __device__ __forceinline__ void km_ticket_finalize(const KmParams &P, int b, flo
     // batched, and the new centroids are staged in shared memory for the table rebuild.
     float *cent = P.cent + (size_t)b * k * D;
     const long long *sums = P.sums + (size_t)b * k * D;
+    const float *affine = P.affine ? P.affine + (size_t)b * D * 2 : nullptr;
     const int my_cnt = lane < k ? __ldcg(P.counts + b * k + lane) : 0;
 #pragma unroll 4
     for (int i0 = 0; i0 < k * D; i0 += 32) {
@@ -216,7 +235,7 @@ __device__ __forceinline__ void km_ticket_finalize(const KmParams &P, int b, flo
         if (ok) {
             const long long s = __ldcg(sums + i);
             float c;
-            if (cnt > 0) c = __double2float_rn(__ddiv_rn((double)s, __dmul_rn((double)cnt, (double)P.fix_scale)));
+            if (cnt > 0) c = km_affine(affine, i % D, __double2float_rn(__ddiv_rn((double)s, __dmul_rn((double)cnt, (double)P.fix_scale))));
             else c = cent[i];
             cent[i] = c;
             s_c[i] = c;
@@ -224,7 +243,7 @@ __device__ __forceinline__ void km_ticket_finalize(const KmParams &P, int b, flo
     }
     if (lane == 0) P.done[b] = 0;
     __syncwarp();
-    km_write_prep(s_c, P.prep + (size_t)b * (D * K + K), D, k, K, lane, 32);
+    km_write_prep(s_c, P.prep + (size_t)b * (D * K + K), D, k, K, lane, 32, affine);
     KM_TR(6);
 }
 
@@ -983,16 +1002,17 @@ __global__ void km_finalize_kernel(const __grid_constant__ KmParams P, int K)
     griddep_wait();                // every atomic of the pass has landed
     float *cent = P.cent + (size_t)b * k * D;
     const long long *sums = P.sums + (size_t)b * k * D;
+    const float *affine = P.affine ? P.affine + (size_t)b * D * 2 : nullptr;
     for (int i = threadIdx.x; i < k * D; i += blockDim.x) {
         const int cnt = P.counts[b * k + i / D];
         float c;
-        if (cnt > 0) c = __double2float_rn(__ddiv_rn((double)sums[i], __dmul_rn((double)cnt, (double)P.fix_scale)));
+        if (cnt > 0) c = km_affine(affine, i % D, __double2float_rn(__ddiv_rn((double)sums[i], __dmul_rn((double)cnt, (double)P.fix_scale))));
         else c = cent[i];
         cent[i] = c;
         s_c[i] = c;
     }
     __syncthreads();
-    km_write_prep(s_c, P.prep + (size_t)b * (D * K + K), D, k, K, threadIdx.x, blockDim.x);
+    km_write_prep(s_c, P.prep + (size_t)b * (D * K + K), D, k, K, threadIdx.x, blockDim.x, affine);
 }
 
 template <int K, int TP, int V>
@@ -1110,7 +1130,7 @@ size_t kmeans_workspace_bytes(int B, int D, int N, int k)
 // d_ws: workspace of kmeans_workspace_bytes(B, D, N, k), 16-byte aligned.
 int kmeans_launch(const float *d_feat, size_t img_stride, int plane_stride, int B, int D, int N, int k, int iters,
                   int fix_shift, const int32_t *d_init_idx, int32_t *d_labels, float *d_centroids, void *d_ws,
-                  cudaStream_t st)
+                  cudaStream_t st, const float *d_affine)
 {
     if (k < 1 || k > 32) return set_error(GCIS_E_INVALID, "kmeans: k=%d outside 1..32", k);
     if (iters < 1) return set_error(GCIS_E_INVALID, "kmeans: iters=%d < 1", iters);
@@ -1127,7 +1147,7 @@ int kmeans_launch(const float *d_feat, size_t img_stride, int plane_stride, int 
     int *done = reinterpret_cast<int *>(w); w += sizeof(int) * (size_t)B;
     unsigned char *lab8 = reinterpret_cast<unsigned char *>(align16(w));
 
-    km_init_kernel<<<B, 256, 0, st>>>(d_feat, img_stride, plane_stride, d_init_idx, cent, prep, sums, counts, done, D, N, k, K);
+    km_init_kernel<<<B, 256, 0, st>>>(d_feat, img_stride, plane_stride, d_init_idx, cent, prep, sums, counts, done, D, N, k, K, d_affine);
     GCIS_LAUNCH_CHECK();
     // 128-bit loads need 16-byte aligned, padded planes; otherwise one pixel per thread
     const bool vec4 = plane_stride % 4 == 0 && plane_stride >= round_up(N, 4) && img_stride % 4 == 0 &&
@@ -1136,6 +1156,7 @@ int kmeans_launch(const float *d_feat, size_t img_stride, int plane_stride, int 
     P.feat = d_feat; P.img_stride = img_stride; P.plane_stride = plane_stride;
     P.cent = cent; P.prep = prep; P.sums = sums; P.counts = counts; P.done = done;
     P.lab8 = lab8; P.lab_stride = (int)km_lab_stride(N);
+    P.affine = d_affine;
     // tile-resident pass when a tile fits twice per SM (GCIS_KM_RING=1 forces the streaming-ring pass)
     const int tp = vec4 ? kt_tile_pixels(K, D) : 0;
     P.D = D; P.N = N; P.k = k; P.chunks = tp ? ceil_div(N, tp) : ceil_div(N, KM_THREADS * (vec4 ? 4 : 1));

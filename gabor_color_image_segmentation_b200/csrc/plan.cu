@@ -39,17 +39,26 @@ int label_metrics_launch(const int32_t *, const uint16_t *, const int32_t *, int
 int find_boundaries_launch(const int32_t *, uint8_t *, int, int, int, cudaStream_t);
 size_t kmeans_workspace_bytes(int B, int D, int N, int k);
 int kmeans_launch(const float *, size_t, int, int, int, int, int, int, int, const int32_t *, int32_t *, float *,
-                  void *, cudaStream_t);
+                  void *, cudaStream_t, const float *d_affine);
+// feature assembly (features.cu): optional smoothing, normalisation statistics
+struct SmoothPlan;
+SmoothPlan *smooth_plan_new(const double *sigmas, int S, int O, int D, int H, int W, double factor);
+void smooth_plan_delete(SmoothPlan *);
+int smooth_launch(SmoothPlan &, float *, size_t, int, float *, int, long long *, float, cudaStream_t);
+int feature_moments_launch(const float *, size_t, int, int, int, int, float, long long *, cudaStream_t);
+int feature_affine_launch(const long long *, float *, int, int, int, float, cudaStream_t);
 GaborLaunchPlan *gabor_plan_new(const GaborBankHost &, int H, int W, int C, int P, int Wp, int feature, size_t *smem);
 void gabor_plan_delete(GaborLaunchPlan *);
-int gabor_launch(GaborLaunchPlan &, const float *, float *, const float *, const GaborScale *, int, int, cudaStream_t);
+int gabor_launch(GaborLaunchPlan &, const float *, float *, const float *, const GaborScale *, int, int, cudaStream_t,
+                 long long *d_stats, float stat_scale);
 // tensor-core row pass (gabor_tc.cu); plan_new returns nullptr when the configuration is not covered
 struct GaborTcPlan;
 GaborTcPlan *gabor_tc_plan_new(const GaborBankHost &, int H, int W, int C, int P, int Wp16, int feature, int colour_space);
 void gabor_tc_plan_delete(GaborTcPlan *);
 size_t gabor_tc_plan_bytes(const GaborTcPlan *);
 int colour_planes16_launch(const uint8_t *, void *, int, int, int, int, int, cudaStream_t);
-int gabor_tc_launch(GaborTcPlan &, const void *, float *, const float *, const GaborScale *, int, int, cudaStream_t);
+int gabor_tc_launch(GaborTcPlan &, const void *, float *, const float *, const GaborScale *, int, int, cudaStream_t,
+                    long long *d_stats, float stat_scale);
 
 }  // namespace gcis
 
@@ -61,6 +70,10 @@ struct gcis_plan {
     GaborBankHost bank;
     GaborLaunchPlan *glp = nullptr;
     GaborTcPlan *gtc = nullptr;  // non-null: the filter bank runs its row pass on the tensor cores
+    SmoothPlan *smooth = nullptr;  // non-null: Gaussian smoothing of the magnitude planes (cfg.smooth > 0)
+    float *d_tmp[2] = {nullptr, nullptr};        // [group][D][N] scratch of the smoothing's row pass
+    long long *d_stats[2] = {nullptr, nullptr};  // [group][D][GB_STAT_SLOTS] integer moments (cfg.normalise)
+    float *d_affine[2] = {nullptr, nullptr};     // [group][D][2] z-score map a, b
     int D = 0, N = 0, Np = 0, P = 0, Wp = 0, Wp16 = 0, group = 1;
     size_t bytes = 0;
     // device workspaces
@@ -153,12 +166,20 @@ int segment_group(gcis_plan *p, int lane, const uint8_t *d_img, int nb, const in
     if (p->gtc) TRY(colour_planes16_launch(d_img, p->d_planes[lane], nb, c.height, c.width, p->P, p->Wp16, st));
     else TRY(colour_planes_launch(d_img, p->d_planes[lane], nb, c.height, c.width, p->P, p->Wp, c.colour_space, st));
     if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 1), st);
-    if (p->gtc) TRY(gabor_tc_launch(*p->gtc, p->d_planes[lane], feat, p->d_taps, p->d_scales, nb, pstride, st));
-    else TRY(gabor_launch(*p->glp, p->d_planes[lane], feat, p->d_taps, p->d_scales, nb, pstride, st));
+    const float stat_scale = (float)(1u << c.fix_shift);
+    const bool norm = c.normalise != 0 && d_labels != nullptr;
+    long long *stats = norm ? p->d_stats[lane] : nullptr;
+    if (norm) GCIS_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(long long) * (size_t)nb * p->D * GB_STAT_SLOTS, st));
+    // the moments are taken from what the clustering will read: in the filter bank's epilogue, or in the smoothing's
+    long long *gabor_stats = p->smooth ? nullptr : stats;
+    if (p->gtc) TRY(gabor_tc_launch(*p->gtc, p->d_planes[lane], feat, p->d_taps, p->d_scales, nb, pstride, st, gabor_stats, stat_scale));
+    else TRY(gabor_launch(*p->glp, p->d_planes[lane], feat, p->d_taps, p->d_scales, nb, pstride, st, gabor_stats, stat_scale));
+    if (p->smooth) TRY(smooth_launch(*p->smooth, feat, (size_t)p->D * pstride, pstride, p->d_tmp[lane], nb, stats, stat_scale, st));
     if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 2), st);
     if (d_labels) {
+        if (norm) TRY(feature_affine_launch(stats, p->d_affine[lane], nb, p->D, p->N, stat_scale, st));
         TRY(kmeans_launch(feat, (size_t)p->D * pstride, pstride, nb, p->D, p->N, c.k, c.iters, c.fix_shift, d_init,
-                          d_labels, nullptr, p->d_km_ws[lane], st));
+                          d_labels, nullptr, p->d_km_ws[lane], st, norm ? p->d_affine[lane] : nullptr));
         if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 3), st);
     }
     return GCIS_OK;
@@ -278,6 +299,9 @@ int32_t gcis_plan_create(const gcis_config *cfg, gcis_plan **out)
     if (cfg->iters < 1) return set_error(GCIS_E_INVALID, "plan: iters=%d", cfg->iters);
     if (cfg->max_gt < 0 || cfg->n_lab_cap < 1) return set_error(GCIS_E_INVALID, "plan: max_gt=%d n_lab_cap=%d", cfg->max_gt, cfg->n_lab_cap);
     if (!(cfg->bandwidth > 0) || !(cfg->n_stds > 0)) return set_error(GCIS_E_INVALID, "plan: bandwidth/n_stds");
+    if (!(cfg->smooth >= 0) || cfg->smooth > 8) return set_error(GCIS_E_INVALID, "plan: smooth=%g outside 0..8", cfg->smooth);
+    if (cfg->normalise && (int64_t)cfg->height * cfg->width > (1 << 25))
+        return set_error(GCIS_E_INVALID, "plan: normalisation supports up to 2^25 pixels per image");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
         return set_error(GCIS_E_CUDA, "plan: no CUDA device (this library has no CPU path)");
@@ -319,6 +343,12 @@ int32_t gcis_plan_create(const gcis_config *cfg, gcis_plan **out)
 
     const size_t MB = cfg->max_batch, G = std::max(cfg->max_gt, 1), k = cfg->k;
     auto fail = [&](int code) { gcis_plan_destroy(p); return code; };
+    if (cfg->smooth > 0) {
+        std::vector<double> sig(cfg->n_scales);
+        for (int si = 0; si < cfg->n_scales; ++si) sig[si] = gabor_sigma(p->freqs[si], cfg->bandwidth);
+        p->smooth = smooth_plan_new(sig.data(), cfg->n_scales, cfg->n_orient, p->D, H, W, cfg->smooth);
+        if (!p->smooth) { set_error(GCIS_E_INVALID, "plan: smoothing set-up failed (radius too large or no memory)"); return fail(GCIS_E_INVALID); }
+    }
 #define PA(ptr, n)                                        \
     do {                                                  \
         int _rc = dev_alloc(&(ptr), (n), &p->bytes);      \
@@ -333,6 +363,11 @@ int32_t gcis_plan_create(const gcis_config *cfg, gcis_plan **out)
         // f32 planes, or bf16 planes (half the bytes) when the tensor cores take the row pass
         PA(p->d_planes[l], p->gtc ? ((size_t)p->group * 3 * H * p->Wp16 + 1) / 2 : (size_t)p->group * 3 * H * p->Wp);
         PA(p->d_feat[l], (size_t)p->group * p->D * p->Np);
+        if (p->smooth) PA(p->d_tmp[l], (size_t)p->group * p->D * p->N);
+        if (cfg->normalise) {
+            PA(p->d_stats[l], (size_t)p->group * p->D * GB_STAT_SLOTS);
+            PA(p->d_affine[l], (size_t)p->group * p->D * 2);
+        }
         char *ws = nullptr;
         int rc2 = dev_alloc(&ws, kmeans_workspace_bytes(p->group, p->D, p->N, cfg->k), &p->bytes);
         if (rc2) return fail(rc2);
@@ -377,6 +412,7 @@ void gcis_plan_destroy(gcis_plan *p)
     cudaFree(p->d_taps); cudaFree(p->d_scales);
     for (int l = 0; l < 2; ++l) {
         cudaFree(p->d_planes[l]); cudaFree(p->d_feat[l]); cudaFree(p->d_km_ws[l]);
+        cudaFree(p->d_tmp[l]); cudaFree(p->d_stats[l]); cudaFree(p->d_affine[l]);
         if (p->lane_done[l]) cudaEventDestroy(p->lane_done[l]);
         if (p->lane_stream[l]) cudaStreamDestroy(p->lane_stream[l]);
     }
@@ -394,6 +430,7 @@ void gcis_plan_destroy(gcis_plan *p)
     if (p->stream) cudaStreamDestroy(p->stream);
     gabor_plan_delete(p->glp);
     gabor_tc_plan_delete(p->gtc);
+    smooth_plan_delete(p->smooth);
     delete p;
 }
 
@@ -428,6 +465,24 @@ int32_t gcis_gabor_features(gcis_plan *p, const uint8_t *d_img, int32_t B, float
     return GCIS_OK;
 }
 
+int32_t gcis_feature_affine(gcis_plan *p, const float *d_feat, int32_t B, float *d_affine, void *stream)
+{
+    TRY(plan_check_batch(p, B));
+    if (!d_feat || !d_affine) return set_error(GCIS_E_INVALID, "feature_affine: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t feat_stride = (size_t)p->D * p->N;
+    const float stat_scale = (float)(1u << p->cfg.fix_shift);
+    for (int b0 = 0; b0 < B; b0 += p->group) {
+        const int nb = std::min(p->group, B - b0);
+        long long *stats = p->d_stats[0];
+        if (!stats) return set_error(GCIS_E_INVALID, "feature_affine: the plan was created without normalise");
+        GCIS_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(long long) * (size_t)nb * p->D * GB_STAT_SLOTS, st));
+        TRY(feature_moments_launch(d_feat + b0 * feat_stride, feat_stride, p->N, nb, p->D, p->N, stat_scale, stats, st));
+        TRY(feature_affine_launch(stats, d_affine + (size_t)b0 * p->D * 2, nb, p->D, p->N, stat_scale, st));
+    }
+    return GCIS_OK;
+}
+
 int32_t gcis_kmeans(gcis_plan *p, const float *d_feat, int32_t B, const int32_t *d_init_idx, int32_t *d_labels,
                     float *d_centroids, void *stream)
 {
@@ -437,9 +492,14 @@ int32_t gcis_kmeans(gcis_plan *p, const float *d_feat, int32_t B, const int32_t 
     const size_t feat_stride = (size_t)p->D * p->N;
     for (int b0 = 0; b0 < B; b0 += p->group) {
         const int nb = std::min(p->group, B - b0);
+        const float *affine = nullptr;
+        if (c.normalise) {   // caller-supplied features: their moments are taken here, then the same folded map
+            TRY(gcis_feature_affine(p, d_feat + b0 * feat_stride, nb, p->d_affine[0], stream));
+            affine = p->d_affine[0];
+        }
         TRY(kmeans_launch(d_feat + b0 * feat_stride, feat_stride, p->N, nb, p->D, p->N, c.k, c.iters, c.fix_shift, d_init_idx + (size_t)b0 * c.k,
                           d_labels + (size_t)b0 * p->N, d_centroids ? d_centroids + (size_t)b0 * c.k * p->D : nullptr,
-                          p->d_km_ws[0], st));
+                          p->d_km_ws[0], st, affine));
     }
     return GCIS_OK;
 }

@@ -74,7 +74,8 @@ class Plan:
 
     def __init__(self, height: int, width: int, max_batch: int = 1, bank: Optional[GaborBank] = None,
                  colour_space: str = "rgb", feature: str = "magnitude", k: int = 8, iters: int = 20,
-                 fix_shift: int = 24, max_gt: int = 5, n_lab_cap: int = 64, dil_recall: int = 5, group: int = 0):
+                 fix_shift: int = 24, max_gt: int = 5, n_lab_cap: int = 64, dil_recall: int = 5, group: int = 0,
+                 normalise: bool = False, smooth: float = 0.0):
         self.lib = _lib.load()
         self.bank = bank or GaborBank.default()
         self.H, self.W, self.N = int(height), int(width), int(height) * int(width)
@@ -85,7 +86,9 @@ class Plan:
         cfg = _lib.GcisConfig(self.H, self.W, self.max_batch, _lib.COLOUR[colour_space],
                               len(self.bank.frequencies), len(self.bank.thetas), self._f, self._t,
                               self.bank.bandwidth, self.bank.n_stds, _lib.FEATURE[feature], self.k, self.iters,
-                              self.fix_shift, self.max_gt, self.n_lab_cap, int(dil_recall), int(group))
+                              self.fix_shift, self.max_gt, self.n_lab_cap, int(dil_recall), int(group),
+                              int(bool(normalise)), float(smooth))
+        self.normalise, self.smooth = bool(normalise), float(smooth)
         h = C.c_void_p()
         _lib.check(self.lib.gcis_plan_create(C.byref(cfg), C.byref(h)), "gcis_plan_create")
         self._h = h
@@ -150,6 +153,18 @@ class Plan:
         _lib.check(self.lib.gcis_kmeans(self._h, feat.data_ptr(), B, idx.data_ptr(), labels.data_ptr(),
                                         cent.data_ptr(), self._stream()), "gcis_kmeans")
         return labels, cent
+
+    def feature_affine(self, feat):
+        """[B,D,2] float32 (a, b) of the per-feature z-score z = a*x + b of a feature tensor (normalise=True plans)."""
+        torch = _torch()
+        if (not feat.is_cuda or feat.dtype != torch.float32 or feat.dim() != 4
+                or tuple(feat.shape[1:]) != (self.D, self.H, self.W) or not 1 <= feat.shape[0] <= self.max_batch):
+            raise ValueError(f"feat must be a CUDA float32 tensor [B<={self.max_batch},{self.D},{self.H},{self.W}]")
+        feat = feat.contiguous()
+        out = torch.empty((feat.shape[0], self.D, 2), dtype=torch.float32, device=feat.device)
+        _lib.check(self.lib.gcis_feature_affine(self._h, feat.data_ptr(), feat.shape[0], out.data_ptr(), self._stream()),
+                   "gcis_feature_affine")
+        return out
 
     def segment(self, img, init_idx):
         torch = _torch()

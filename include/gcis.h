@@ -45,7 +45,7 @@ extern "C" {
 #define GCIS_API
 #endif
 
-#define GCIS_VERSION 100
+#define GCIS_VERSION 101
 
 #define GCIS_OK 0
 #define GCIS_E_INVALID (-1) /* bad argument                                   */
@@ -96,6 +96,9 @@ typedef struct gcis_config {
     int32_t n_lab_cap;     /* capacity for max(gt)+1                        */
     int32_t dil_recall;    /* `size` of set_boundary_recall (default 5)     */
     int32_t group;         /* images per launch group, 0 = auto (64; sized for occupancy, not for L2 residency) */
+    /* feature assembly options (north_star "optional smoothing and normalisation") */
+    int32_t normalise;     /* 1: cluster on per-feature z-scores (folded into the k-means score table) */
+    double smooth;         /* > 0: Gaussian smoothing of every magnitude plane, sigma = smooth * sigma_s  */
 } gcis_config;
 
 typedef struct gcis_plan gcis_plan;
@@ -138,6 +141,11 @@ GCIS_API int32_t gcis_plan_uses_tensor_cores(const gcis_plan *plan);
 GCIS_API int32_t gcis_gabor_features(gcis_plan *plan, const uint8_t *d_img, int32_t B, float *d_feat, void *stream);
 GCIS_API int32_t gcis_kmeans(gcis_plan *plan, const float *d_feat, int32_t B, const int32_t *d_init_idx,
                     int32_t *d_labels, float *d_centroids, void *stream);
+/* Per-feature normalisation map of a feature tensor (plans created with normalise = 1):
+ * d_affine [B][D][2] float32 {a_d, b_d} with z_d = a_d * x_d + b_d = (x_d - mean_d) / std_d over the image,
+ * mean and std from exact integer moments; a = b = 0 for a constant plane.  With normalise = 1
+ * gcis_kmeans / gcis_segment_device cluster on z and d_centroids are centroids in z space. */
+GCIS_API int32_t gcis_feature_affine(gcis_plan *plan, const float *d_feat, int32_t B, float *d_affine, void *stream);
 GCIS_API int32_t gcis_segment_device(gcis_plan *plan, const uint8_t *d_img, int32_t B, const int32_t *d_init_idx,
                             int32_t *d_labels, void *stream);
 

@@ -291,10 +291,52 @@ ORC_API void orc_conv_sep_complex_reflect(const double *img, int H, int W,
  *   c_jd <- (float)((double)sum_jd / ((double)count_j * 2^fix_shift)); empty cluster keeps c_jd
  * feat is planar [D][N]; centroids [k][D]; k <= 64.
  */
+/* Per-feature normalisation map: z_d = a_d x_d + b_d = (x_d - mean_d) / std_d over the image, from
+ * EXACT integer moments so that the result does not depend on any summation order:
+ *   S1 = sum_p lrintf(x * 2^fix_shift) (int64),  S2 = sum_p lrintf(x * 2^16)^2 kept as two int64 partial sums of
+ *   the low 32 bits and of the remaining high bits of every square, S2 = (double)hi * 2^32 + (double)lo
+ *   mean = S1 / (N 2^fix_shift),  E[x^2] = S2 / (N 2^32),  var = max(E[x^2] - mean^2, 0)   (double)
+ *   a = (float)(1 / sqrt(var)), b = (float)(-mean / sqrt(var));  a = b = 0 when sqrt(var) <= 1e-12.
+ * affine is [D][2]. */
+ORC_API void orc_feature_affine(const float *feat, int D, int64_t N, int fix_shift, float *affine)
+{
+    const float fix_scale = (float)(1u << fix_shift);
+    for (int d = 0; d < D; ++d) {
+        const float *x = feat + (size_t)d * N;
+        int64_t s1 = 0, lo = 0, hi = 0;
+        for (int64_t p = 0; p < N; ++p) {
+            int64_t r = (int64_t)__builtin_lrintf(x[p] * 65536.0f);
+            uint64_t r2 = (uint64_t)(r * r);
+            s1 += (int64_t)__builtin_lrintf(x[p] * fix_scale);
+            lo += (int64_t)(r2 & 0xffffffffull);
+            hi += (int64_t)(r2 >> 32);
+        }
+        double mean = (double)s1 / ((double)N * (double)fix_scale);
+        double ex2 = ((double)hi * 4294967296.0 + (double)lo) / ((double)N * 4294967296.0);
+        double var = ex2 - mean * mean;
+        if (var < 0.0) var = 0.0;
+        double sd = sqrt(var);
+        float a = 0.f, b = 0.f;
+        if (sd > 1e-12) { a = (float)(1.0 / sd); b = (float)(-mean / sd); }
+        affine[2 * d] = a; affine[2 * d + 1] = b;
+    }
+}
+
+/* centroid in the clustered space from its x-space value: (float)fma((double)a, (double)cx, (double)b) */
+static inline float km_affine(const float *affine, int d, float cx)
+{
+    if (!affine) return cx;
+    return (float)__builtin_fma((double)affine[2 * d], (double)cx, (double)affine[2 * d + 1]);
+}
+
+/* orc_kmeans with the optional normalisation folded into the score table (affine may be NULL):
+ *   c_jd (z space) = km_affine(cx_jd);  m_jd = a_d * (-2 c_jd) (fp32);
+ *   cn_j = (float) sum_d [ (double)c_jd^2 + (double)b_d * (double)(-2 c_jd) ]  (d ascending, c^2 first)
+ *   score and update as in orc_kmeans, on the RAW features. */
 ORC_CLONES
-ORC_API void orc_kmeans(const float *feat, int D, int64_t N, int k, int T, int fix_shift,
-                        const int32_t *init_idx, int32_t *labels, float *centroids,
-                        int64_t *counts_out)
+ORC_API void orc_kmeans_affine(const float *feat, int D, int64_t N, int k, int T, int fix_shift,
+                               const int32_t *init_idx, const float *affine, int32_t *labels, float *centroids,
+                               int64_t *counts_out)
 {
     const float fix_scale = (float)(1u << fix_shift);
     float *m = malloc(sizeof(float) * (size_t)k * D);
@@ -303,15 +345,20 @@ ORC_API void orc_kmeans(const float *feat, int D, int64_t N, int k, int T, int f
     int64_t *cnt = malloc(sizeof(int64_t) * (size_t)k);
     float *s = malloc(sizeof(float) * (size_t)k * KM_BLK);
     for (int j = 0; j < k; ++j)
-        for (int d = 0; d < D; ++d) centroids[(size_t)j * D + d] = feat[(size_t)d * N + init_idx[j]];
+        for (int d = 0; d < D; ++d) centroids[(size_t)j * D + d] = km_affine(affine, d, feat[(size_t)d * N + init_idx[j]]);
 
     for (int t = 0; t < T; ++t) {
         for (int j = 0; j < k; ++j) {
             double acc = 0.0;
             for (int d = 0; d < D; ++d) {
                 float c = centroids[(size_t)j * D + d];
-                m[(size_t)j * D + d] = -2.0f * c;
+                float mm = -2.0f * c;
                 acc += (double)c * (double)c;
+                if (affine) {
+                    acc += (double)affine[2 * d + 1] * (-2.0 * (double)c);
+                    mm = affine[2 * d] * mm;
+                }
+                m[(size_t)j * D + d] = mm;
             }
             cn[j] = (float)acc;
         }
@@ -350,11 +397,18 @@ ORC_API void orc_kmeans(const float *feat, int D, int64_t N, int k, int T, int f
             if (cnt[j] == 0) continue;
             double den = (double)cnt[j] * (double)fix_scale;
             for (int d = 0; d < D; ++d)
-                centroids[(size_t)j * D + d] = (float)((double)sums[(size_t)j * D + d] / den);
+                centroids[(size_t)j * D + d] = km_affine(affine, d, (float)((double)sums[(size_t)j * D + d] / den));
         }
     }
     if (counts_out) memcpy(counts_out, cnt, sizeof(int64_t) * (size_t)k);
     free(m); free(cn); free(sums); free(cnt); free(s);
+}
+
+ORC_API void orc_kmeans(const float *feat, int D, int64_t N, int k, int T, int fix_shift,
+                        const int32_t *init_idx, int32_t *labels, float *centroids,
+                        int64_t *counts_out)
+{
+    orc_kmeans_affine(feat, D, N, k, T, fix_shift, init_idx, NULL, labels, centroids, counts_out);
 }
 
 /* One assignment pass only (teacher-forced tests): labels + best/second-best

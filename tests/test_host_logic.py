@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), n
         assert n in _lib.SIGNATURES, "no ctypes signature for " + n
     assert set(_lib.SIGNATURES) == set(names)
-    assert lib.gcis_version() == 100
+    assert lib.gcis_version() == 101
 
 
 def test_sass_is_sm100a():

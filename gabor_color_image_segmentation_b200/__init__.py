@@ -13,7 +13,9 @@ from .metrics import metrics, finish_image, find_boundaries
 from .engine import GaborBank, Plan, BatchCounts, kmeans_init_indices, label_counts_host
 from .segment import gabor_kmeans_segment
 from .region_scores import region_scores
+from .dataset import evaluate_dataset, print_like_script
 
 __all__ = ["metrics", "get_segmentation", "get_segment_from_filename", "gabor_kmeans_segment",
            "GaborBank", "Plan", "BatchCounts", "kmeans_init_indices", "label_counts_host",
-           "pack_ground_truths", "finish_image", "find_boundaries", "region_scores"]
+           "pack_ground_truths", "finish_image", "find_boundaries", "region_scores",
+           "evaluate_dataset", "print_like_script"]

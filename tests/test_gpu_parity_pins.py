@@ -185,7 +185,7 @@ def test_real_fixture_segmenter_against_oracle():
         Hh, Ww = img.shape[:2]
         plan = plans.setdefault((Hh, Ww), Plan(Hh, Ww, max_batch=1, k=K, iters=T, max_gt=0))
         idx = orc.kmeans_init_indices(Hh * Ww, K, n)[None]
-        d_img = torch.from_numpy(np.ascontiguousarray(img)[None]).cuda()
+        d_img = torch.from_numpy(np.array(img)[None]).cuda()
         feat = plan.gabor_features(d_img).cpu().numpy()[0]
         want = orc.gabor_features(img)
         tol = 1e-5 * np.abs(want).max() + 1e-5 * np.abs(want)
@@ -196,3 +196,36 @@ def test_real_fixture_segmenter_against_oracle():
         ref = gold[fid + "/labels"]
         dis = np.flatnonzero(ref.ravel() != labels.ravel())
         assert len(dis) <= 2e-3 * ref.size, (fid, len(dis))
+
+
+def test_evaluate_dataset_on_the_real_fixture(capsys):
+    """script.py:19-38 over a directory, batched: JPEG decode + .mat parsing in a thread pool into pinned buffers,
+    one plan per image shape.  Every per-image dict equals the drop-in per-image path (segmenter slot + metrics
+    class), the printout has the reference's format, and the labels agree with the committed oracle labels."""
+    from gabor_color_image_segmentation_b200 import evaluate_dataset, print_like_script, gabor_kmeans_segment, metrics
+    gold, items = _real()
+    res = evaluate_dataset(os.path.join(FIX, "images"), os.path.join(FIX, "truth"), k=K, iters=T, want_labels=True)
+    order = sorted(str(f) for f in gold["ids"])
+    assert [r[0] for r in res] == order and len(res) == 8
+    by_id = {fid: (img, gts) for _, fid, img, gts in items}
+    for i, (fid, m, labels) in enumerate(res):
+        img, gts = by_id[fid]
+        lab1 = gabor_kmeans_segment(img, n_clusters=K, n_iter=T, seed=i)        # same seed convention: sorted position
+        np.testing.assert_array_equal(labels, lab1)
+        one = metrics(img, lab1, gts)
+        one.set_metrics()
+        want = one.get_metrics()
+        for key in want:
+            assert float(m[key]) == float(want[key]), (fid, key)
+    capsys.readouterr()
+    print_like_script(res[:1])
+    one = metrics(by_id[res[0][0]][0], res[0][2], by_id[res[0][0]][1]); one.set_metrics()
+    got = capsys.readouterr().out.splitlines()
+    one.display_metrics()
+    ref_line = capsys.readouterr().out.splitlines()[0]
+    assert got[0] == "Processing image " + res[0][0] and got[1] == ref_line
+    # subset selection and the oracle labels of the fixture (those were seeded by the fixture's own order)
+    sub = evaluate_dataset(os.path.join(FIX, "images"), os.path.join(FIX, "truth"), names=["3096"], k=K, iters=T, seed=2,
+                           want_labels=True)
+    assert len(sub) == 1 and sub[0][0] == "3096"
+    assert (sub[0][2] != gold["3096/labels"]).mean() <= 2e-3

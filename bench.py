@@ -517,6 +517,95 @@ def make_data_indices(indices, workers=None):
     return np.stack(imgs), np.stack(gts)
 
 
+CONFIGS = {
+    # name: (H, W, k, images, colour space, dense bank, BASELINE.json config it belongs to)
+    "k16": (321, 481, 16, 64, "rgb", False, "configs[1] shape with k=16"),
+    "k32": (1024, 1024, 32, 8, "rgb", False, "configs[3]: 1024x1024 RGB, k-means k=32"),
+    "k32_4k": (2160, 3840, 32, 2, "rgb", False, "configs[3]: 3840x2160 RGB, k-means k=32"),
+    "dense": (321, 481, 8, 32, "opponent", True, "configs[2]: dense bank 8 scales x 12 orientations on opponent channels (D = 288)"),
+    "dense_lab": (321, 481, 8, 32, "lab", True, "configs[2]: dense bank 8 scales x 12 orientations on Lab channels (D = 288)"),
+    "normalised": (321, 481, 8, 200, "rgb", False, "configs[1] with per-feature normalisation (DESIGN.md 3.6)"),
+    "smoothed": (321, 481, 8, 100, "rgb", False, "configs[1] with feature smoothing 0.5 sigma_s and normalisation"),
+}
+
+
+def run_config(args):
+    """Secondary BASELINE configurations as driver-visible records: one JSON line with the stage times of a
+    device-resident pass (CUDA events inside the library, single-stream plan) and each stage's roofline fraction."""
+    import torch
+    from gabor_color_image_segmentation_b200 import GaborBank, Plan
+    from gabor_color_image_segmentation_b200.pipeline import init_indices_for
+    from gabor_color_image_segmentation_b200.synth import synth_image, synth_ground_truths
+    Hc, Wc, k, B, space, dense, what = CONFIGS[args.config]
+    B = args.images if args.images != 200 or args.config in ("normalised",) else B
+    os.environ["GCIS_LANES"] = "1"
+    torch.cuda.set_device(0)
+    small = max(1, max(Hc, Wc) // 1024)                      # large images: upscaled synthetic content + noise
+    rng = np.random.default_rng(5)
+    imgs, gts = [], []
+    for i in range(min(B, 8)):
+        im = synth_image(300 + i, Hc // small, Wc // small)
+        gt = synth_ground_truths(300 + i, Hc // small, Wc // small, 1)
+        if small > 1:
+            im = np.kron(im, np.ones((small, small, 1), np.uint8))[:Hc, :Wc]
+            im = (im.astype(np.int16) + rng.integers(-10, 11, im.shape)).clip(0, 255).astype(np.uint8)
+            gt = np.kron(gt, np.ones((1, small, small), np.uint16))[:, :Hc, :Wc]
+        imgs.append(np.ascontiguousarray(im)); gts.append(np.ascontiguousarray(gt))
+    imgs = np.stack([imgs[i % len(imgs)] for i in range(B)]); gts = np.stack([gts[i % len(gts)] for i in range(B)])
+    kw = {}
+    if dense:
+        kw["bank"] = GaborBank.dense()
+    if args.config == "normalised":
+        kw["normalise"] = True
+    if args.config == "smoothed":
+        kw.update(normalise=True, smooth=0.5)
+    plan = Plan(Hc, Wc, max_batch=B, k=k, iters=ITERS, max_gt=1, colour_space=space, n_lab_cap=64, **kw)
+    idx = init_indices_for(range(B), Hc * Wc, k)
+    d_img = torch.from_numpy(imgs).cuda(); d_gt = torch.from_numpy(gts.view(np.int16)).cuda(); d_idx = torch.from_numpy(idx).cuda()
+    for _ in range(max(args.warmup, 3)):
+        plan.pipeline_device(d_img, d_gt, d_idx); plan.fetch()
+    sampler = ClockSampler(0); sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        plan.pipeline_device(d_img, d_gt, d_idx); plan.fetch()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.summary()
+    plan.set_profiling(True)
+    plan.pipeline_device(d_img, d_gt, d_idx); plan.fetch()
+    st = plan.last_stage_ms()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    fma = measure_fma_peak()
+    fp32 = fma.get("ffma_rrr_tflops") or 72.5
+    N, D = Hc * Wc, plan.D
+    K = 8 if k <= 8 else (16 if k <= 16 else 32)
+    km_bytes = B * ITERS * N * D * 4.0
+    km_flop = B * ITERS * N * 2.0 * K * D                      # score FMAs actually executed (clusters padded to K)
+    t_hbm, t_fp = km_bytes / (hbm * 1e9), km_flop / (fp32 * 1e12)
+    km_s = st["kmeans"] * 1e-3
+    line = {"metric": METRIC, "value": B / (ms * 1e-3), "unit": "images/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: %d images of %dx%d, D=%d, k=%d, T=%d, colour=%s" % (what, B, Hc, Wc, D, k, ITERS, space),
+                       "name": args.config, "images_per_launch": plan.launch_group(B), "tensor_core_row_pass": plan.uses_tensor_cores},
+            "stage_ms_per_step": st, "clocks": clocks,
+            "roofline": {"kernel": "k-means passes", "bound": "hbm" if t_hbm >= t_fp else "fp32",
+                         "achieved": km_bytes / km_s / 1e9 if t_hbm >= t_fp else km_flop / km_s / 1e12,
+                         "peak": hbm if t_hbm >= t_fp else fp32, "unit": "GB/s" if t_hbm >= t_fp else "TFLOP/s",
+                         "frac": max(t_hbm, t_fp) / km_s, "hbm_gbs": km_bytes / km_s / 1e9, "fp32_tflops": km_flop / km_s / 1e12,
+                         "traffic": None},
+            "gabor_us_per_image": st["gabor"] * 1e3 / B, "fma_peak": fma}
+    print(json.dumps(line))
+    return 0
+
+
 def one_image_latency(img, gts, reps=20):
     """BASELINE config 1 through the drop-in surface: one script.py iteration = labels = segmenter(img);
     metrics(img, labels, gts).set_metrics().  Host arrays in, floats out; median wall-clock ms."""
@@ -566,11 +655,15 @@ def main():
                     help="weak: --images per GPU per step (default, BASELINE configs[1]); strong: one fixed --total-images batch "
                          "sharded over the GPUs (BASELINE configs[4])")
     ap.add_argument("--total-images", type=int, default=10000, help="size of the fixed batch in strong-scaling mode")
+    ap.add_argument("--config", default="headline", choices=["headline"] + sorted(CONFIGS),
+                    help="headline = BASELINE configs[1] (the metric's configuration); the others are the secondary configurations")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if args.scaling == "strong":
         return run_gpu_strong(args)
+    if args.config != "headline":
+        return run_config(args)
     return run_gpu(args)
 
 

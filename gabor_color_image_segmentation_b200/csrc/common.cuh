@@ -56,32 +56,30 @@ struct SmemAttrCache {
     }
 };
 
-// Exact integer moments of a feature plane for the normalisation, per plane GB_STAT_SLOTS int64:
-//   [0] sum rint(x 2^fix_shift)   [1] sum of the low 32 bits of r^2   [2] sum of the high bits of r^2,  r = rint(x 2^16)
-// (r^2 < 2^46 for |x| < 128, so the two partial sums stay below 2^57 / 2^39 for images of up to 2^25 pixels)
+// Exact integer moments of a feature plane for the normalisation, per plane GB_STAT_SLOTS int64, with
+// r = rint(x 2^16):   [0] sum r   [1] sum of the low 32 bits of the partial sums of r^2   [2] sum of their high bits.
+// A thread accumulates a few dozen values (|r| < 2^23 for |x| < 128: sum r fits 32 bits, sum r^2 fits 64), a warp
+// flushes its total split in two words, so that the global sums stay exact for images of up to 2^25 pixels.
 constexpr int GB_STAT_SLOTS = 3;
 #ifdef __CUDACC__
-__device__ __forceinline__ void stat_add(float v, float stat_scale, long long &m1, long long &m2, long long &m3)
+__device__ __forceinline__ void stat_add(float v, int &m1, unsigned long long &m2)
 {
-    const long long r = __float2int_rn(v * 65536.0f);
-    const unsigned long long r2 = (unsigned long long)(r * r);
-    m1 += __float2int_rn(v * stat_scale);
-    m2 += (long long)(r2 & 0xffffffffull);
-    m3 += (long long)(r2 >> 32);
+    const int r = __float2int_rn(v * 65536.0f);
+    m1 += r;
+    m2 += (unsigned long long)((long long)r * r);      // one 32 x 32 -> 64 multiply-add
 }
-__device__ __forceinline__ void stat_flush(long long *dst, long long m1, long long m2, long long m3, int lane)
+__device__ __forceinline__ void stat_flush(long long *dst, long long m1, unsigned long long m2, int lane)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         m1 += __shfl_down_sync(0xffffffffu, m1, o);
         m2 += __shfl_down_sync(0xffffffffu, m2, o);
-        m3 += __shfl_down_sync(0xffffffffu, m3, o);
     }
-    if (lane == 0 && (m1 | m2 | m3)) {
+    if (lane == 0 && (m1 | (long long)m2)) {
         unsigned long long *st = reinterpret_cast<unsigned long long *>(dst);
         atomicAdd(st, (unsigned long long)m1);
-        atomicAdd(st + 1, (unsigned long long)m2);
-        atomicAdd(st + 2, (unsigned long long)m3);
+        atomicAdd(st + 1, m2 & 0xffffffffull);
+        atomicAdd(st + 2, m2 >> 32);
     }
 }
 #endif

@@ -7,7 +7,7 @@
 //                  envelope of scale s), truncated at ceil(3 sigma), taps normalised to sum 1, 'reflect' borders;
 //                  separable: row pass then column pass, fp32.
 //   normalisation  z_d = (x_d - mean_d) / std_d over the image, with mean and std from EXACT integer moments
-//                  S1 = sum rint(x 2^fix_shift), S2 = sum rint(x 2^16)^2 (order-independent, so bit-identical for any
+//                  S1 = sum r, S2 = sum r^2, r = rint(x 2^16) (order-independent, so bit-identical for any
 //                  grid and on the CPU checker); the map z = a x + b is never applied to the feature tensor: the
 //                  k-means kernels fold it into their score table (kmeans.cu), so it costs no HBM traffic.
 #include <math.h>
@@ -102,28 +102,44 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_cols_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < RPT; ++i) acc[i] = fmaf(g, col[(i + t) * SC_COLS], acc[i]);
     }
-    long long m1 = 0, m2 = 0, m3 = 0;
+    int m1 = 0;
+    unsigned long long m2 = 0;
     float *dst = P.out + (size_t)b * P.out_img_stride + (size_t)d * P.out_plane_stride;
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
         const int y = y0 + warp * RPT + i;
         if (y < P.H && x0 + lane < P.W) {
             dst[(size_t)y * P.W + x0 + lane] = acc[i];
-            stat_add(acc[i], P.stat_scale, m1, m2, m3);
+            stat_add(acc[i], m1, m2);
         }
     }
-    if (P.stats) stat_flush(P.stats + ((size_t)b * P.D + d) * GB_STAT_SLOTS, m1, m2, m3, lane);
+    if (P.stats) stat_flush(P.stats + ((size_t)b * P.D + d) * GB_STAT_SLOTS, m1, m2, lane);
 }
 
-// moments of planes somebody else produced (caller-supplied feature tensors): one CTA per (plane, image)
+// moments of finished planes (the default normalisation path, and caller-supplied feature tensors): a streaming
+// read of the features, CTAs = (plane segment, plane, image); 128-bit loads when the planes are 16-byte aligned
+constexpr int FM_SEG = 8192;     // pixels per CTA
 __global__ void __launch_bounds__(256) feature_moments_kernel(const float *__restrict__ feat, size_t img_stride, int plane_stride,
-                                                              int D, int N, float stat_scale, long long *stats)
+                                                              int D, int N, float stat_scale, long long *stats, int vec4)
 {
-    const int d = blockIdx.x, b = blockIdx.y;
+    const int d = blockIdx.y, b = blockIdx.z;
     const float *x = feat + (size_t)b * img_stride + (size_t)d * plane_stride;
-    long long m1 = 0, m2 = 0, m3 = 0;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) stat_add(x[i], stat_scale, m1, m2, m3);
-    stat_flush(stats + ((size_t)b * D + d) * GB_STAT_SLOTS, m1, m2, m3, threadIdx.x & 31);
+    const int p0 = blockIdx.x * FM_SEG, p1 = min(N, p0 + FM_SEG);
+    int m1 = 0;                   // <= 32 values per thread: the 32-bit / 64-bit partial sums are safe (common.cuh)
+    unsigned long long m2 = 0;
+    if (vec4) {
+        for (int i = p0 + 4 * threadIdx.x; i < p1; i += 4 * 256) {
+            if (i + 4 <= p1) {
+                const float4 v = *reinterpret_cast<const float4 *>(x + i);
+                stat_add(v.x, m1, m2); stat_add(v.y, m1, m2); stat_add(v.z, m1, m2); stat_add(v.w, m1, m2);
+            } else {
+                for (int j = i; j < p1; ++j) stat_add(x[j], m1, m2);
+            }
+        }
+    } else {
+        for (int i = p0 + threadIdx.x; i < p1; i += 256) stat_add(x[i], m1, m2);
+    }
+    stat_flush(stats + ((size_t)b * D + d) * GB_STAT_SLOTS, m1, m2, threadIdx.x & 31);
 }
 
 // moments -> the affine map of the z-score, z = a x + b (a = b = 0 for a constant plane)
@@ -133,7 +149,7 @@ __global__ void feature_affine_kernel(const long long *__restrict__ stats, float
     if (i >= n) return;
     const double dn = (double)N;
     const long long *m = stats + (size_t)i * GB_STAT_SLOTS;
-    const double mean = __ddiv_rn((double)m[0], __dmul_rn(dn, (double)stat_scale));
+    const double mean = __ddiv_rn((double)m[0], __dmul_rn(dn, 65536.0));
     const double s2 = __dadd_rn(__dmul_rn((double)m[2], 4294967296.0), (double)m[1]);   // sum r^2, r = rint(x 2^16)
     const double ex2 = __ddiv_rn(s2, __dmul_rn(dn, 4294967296.0));
     double var = __dsub_rn(ex2, __dmul_rn(mean, mean));
@@ -227,7 +243,8 @@ int smooth_launch(SmoothPlan &sp, float *d_feat, size_t img_stride, int plane_st
 int feature_moments_launch(const float *d_feat, size_t img_stride, int plane_stride, int B, int D, int N, float stat_scale,
                            long long *d_stats, cudaStream_t st)
 {
-    feature_moments_kernel<<<dim3(D, B), 256, 0, st>>>(d_feat, img_stride, plane_stride, D, N, stat_scale, d_stats);
+    const int vec4 = plane_stride % 4 == 0 && img_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(d_feat) & 15) == 0;
+    feature_moments_kernel<<<dim3(ceil_div(N, FM_SEG), D, B), 256, 0, st>>>(d_feat, img_stride, plane_stride, D, N, stat_scale, d_stats, vec4);
     GCIS_LAUNCH_CHECK();
     return GCIS_OK;
 }

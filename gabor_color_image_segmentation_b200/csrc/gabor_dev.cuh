@@ -41,7 +41,7 @@ struct GaborParams {
     int tap_slot;                // floats reserved per staged filter (complex, interleaved) in shared memory
     int rowtab_cap;
     // per-plane moments for the optional normalisation, accumulated in the epilogue:
-    // [B][D]{sum q, sum lo32(r^2), sum hi32(r^2)} with q = rint(x 2^fix_shift), r = rint(x 2^16) (GB_STAT_SLOTS = 3)
+    // [B][D][GB_STAT_SLOTS] (common.cuh)
     long long *stats;            // null = not requested
     float stat_scale;            // 2^fix_shift
 };
@@ -320,7 +320,8 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
     const int nrb = (th + GB_RC - 1) / GB_RC;
     const bool col_ok = x0 + lane < P.W;
     const u64 *Tl = reinterpret_cast<const u64 *>(T) + lane;
-    long long m1[2] = {0, 0}, m2[2] = {0, 0}, m3[2] = {0, 0};   // exact integer moments of what this thread writes (normalisation)
+    int m1[2] = {0, 0};                      // exact integer moments of what this thread writes (normalisation)
+    unsigned long long m2[2] = {0, 0};
     for (int rb = warp; rb < nrb; rb += nwarps) {
         u64 Pv[GB_RC], Qv[GB_RC];
         float Sv[GB_RC];
@@ -352,13 +353,13 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
                 const size_t o = (size_t)(y0 + r) * P.W + x0 + lane;
                 const float v0 = P.feature == GCIS_FEATURE_MAGNITUDE ? fast_sqrt(e0) : e0;
                 feat0[o] = v0;
-                if (st0) stat_add(v0, P.stat_scale, m1[0], m2[0], m3[0]);
+                if (st0) stat_add(v0, m1[0], m2[0]);
                 if (feat1) {
                     const float re1 = A + Bv, im1 = Dv - Cv;
                     const float e1 = fmaf(re1, re1, im1 * im1);
                     const float v1 = P.feature == GCIS_FEATURE_MAGNITUDE ? fast_sqrt(e1) : e1;
                     feat1[o] = v1;
-                    if (st1) stat_add(v1, P.stat_scale, m1[1], m2[1], m3[1]);
+                    if (st1) stat_add(v1, m1[1], m2[1]);
                 }
             }
         }
@@ -368,7 +369,7 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
         for (int pl = 0; pl < 2; ++pl) {
             long long *dst = pl ? st1 : st0;
             if (!dst) continue;
-            stat_flush(dst, m1[pl], m2[pl], m3[pl], lane);
+            stat_flush(dst, m1[pl], m2[pl], lane);
         }
     }
 }

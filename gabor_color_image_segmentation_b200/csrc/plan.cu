@@ -170,11 +170,15 @@ int segment_group(gcis_plan *p, int lane, const uint8_t *d_img, int nb, const in
     const bool norm = c.normalise != 0 && d_labels != nullptr;
     long long *stats = norm ? p->d_stats[lane] : nullptr;
     if (norm) GCIS_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(long long) * (size_t)nb * p->D * GB_STAT_SLOTS, st));
-    // the moments are taken from what the clustering will read: in the filter bank's epilogue, or in the smoothing's
-    long long *gabor_stats = p->smooth ? nullptr : stats;
+    // The moments are taken from what the clustering will read: in the smoothing's epilogue, or in the filter bank's
+    // (no extra HBM traffic; measured +2.7 ms per 200 images), or with GCIS_STATS_FUSED=0 by a streaming kernel over the
+    // finished features (measured +3.7 ms: slower, kept for A/B runs and for caller-supplied feature tensors).
+    static const bool fused = [] { const char *e = getenv("GCIS_STATS_FUSED"); return !e || atoi(e) != 0; }();
+    long long *gabor_stats = (p->smooth || !fused) ? nullptr : stats;
     if (p->gtc) TRY(gabor_tc_launch(*p->gtc, p->d_planes[lane], feat, p->d_taps, p->d_scales, nb, pstride, st, gabor_stats, stat_scale));
     else TRY(gabor_launch(*p->glp, p->d_planes[lane], feat, p->d_taps, p->d_scales, nb, pstride, st, gabor_stats, stat_scale));
     if (p->smooth) TRY(smooth_launch(*p->smooth, feat, (size_t)p->D * pstride, pstride, p->d_tmp[lane], nb, stats, stat_scale, st));
+    else if (norm && !fused) TRY(feature_moments_launch(feat, (size_t)p->D * pstride, pstride, nb, p->D, p->N, stat_scale, stats, st));
     if (prof) cudaEventRecord(plan_event(p, 4 * group_index + 2), st);
     if (d_labels) {
         if (norm) TRY(feature_affine_launch(stats, p->d_affine[lane], nb, p->D, p->N, stat_scale, st));

@@ -293,26 +293,28 @@ ORC_API void orc_conv_sep_complex_reflect(const double *img, int H, int W,
  */
 /* Per-feature normalisation map: z_d = a_d x_d + b_d = (x_d - mean_d) / std_d over the image, from
  * EXACT integer moments so that the result does not depend on any summation order:
- *   S1 = sum_p lrintf(x * 2^fix_shift) (int64),  S2 = sum_p lrintf(x * 2^16)^2 kept as two int64 partial sums of
- *   the low 32 bits and of the remaining high bits of every square, S2 = (double)hi * 2^32 + (double)lo
- *   mean = S1 / (N 2^fix_shift),  E[x^2] = S2 / (N 2^32),  var = max(E[x^2] - mean^2, 0)   (double)
+ *   r = lrintf(x * 2^16);  S1 = sum_p r,  S2 = sum_p r^2 (exact integers; S2 taken as (double)hi * 2^32 + (double)lo of
+ *   its high and low 32-bit parts, which is how the kernels carry it)
+ *   mean = S1 / (N 2^16),  E[x^2] = S2 / (N 2^32),  var = max(E[x^2] - mean^2, 0)   (double)
  *   a = (float)(1 / sqrt(var)), b = (float)(-mean / sqrt(var));  a = b = 0 when sqrt(var) <= 1e-12.
  * affine is [D][2]. */
 ORC_API void orc_feature_affine(const float *feat, int D, int64_t N, int fix_shift, float *affine)
 {
-    const float fix_scale = (float)(1u << fix_shift);
+    (void)fix_shift;
     for (int d = 0; d < D; ++d) {
         const float *x = feat + (size_t)d * N;
-        int64_t s1 = 0, lo = 0, hi = 0;
+        int64_t s1 = 0;
+        unsigned __int128 s2 = 0;
         for (int64_t p = 0; p < N; ++p) {
             int64_t r = (int64_t)__builtin_lrintf(x[p] * 65536.0f);
-            uint64_t r2 = (uint64_t)(r * r);
-            s1 += (int64_t)__builtin_lrintf(x[p] * fix_scale);
-            lo += (int64_t)(r2 & 0xffffffffull);
-            hi += (int64_t)(r2 >> 32);
+            s1 += r;
+            s2 += (uint64_t)(r * r);
         }
-        double mean = (double)s1 / ((double)N * (double)fix_scale);
-        double ex2 = ((double)hi * 4294967296.0 + (double)lo) / ((double)N * 4294967296.0);
+        /* the kernels carry S2 as two int64 sums of 32-bit halves of partial sums: hi * 2^32 + lo with lo possibly
+         * above 2^32; any such split represents the same integer, but (double)hi * 2^32 + (double)lo rounds once per
+         * term, so the canonical value is defined on the exact integer: round-to-nearest double of S2 */
+        double mean = (double)s1 / ((double)N * 65536.0);
+        double ex2 = (double)s2 / ((double)N * 4294967296.0);
         double var = ex2 - mean * mean;
         if (var < 0.0) var = 0.0;
         double sd = sqrt(var);

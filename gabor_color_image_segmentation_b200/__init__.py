@@ -14,8 +14,9 @@ from .engine import GaborBank, Plan, BatchCounts, kmeans_init_indices, label_cou
 from .segment import gabor_kmeans_segment
 from .region_scores import region_scores
 from .dataset import evaluate_dataset, print_like_script
+from .decode import decode_jpeg_batch, imread_gpu, jpeg_info
 
 __all__ = ["metrics", "get_segmentation", "get_segment_from_filename", "gabor_kmeans_segment",
            "GaborBank", "Plan", "BatchCounts", "kmeans_init_indices", "label_counts_host",
            "pack_ground_truths", "finish_image", "find_boundaries", "region_scores",
-           "evaluate_dataset", "print_like_script"]
+           "evaluate_dataset", "print_like_script", "decode_jpeg_batch", "imread_gpu", "jpeg_info"]

@@ -38,10 +38,12 @@ def _find_truth(truth_dir: str, name: str) -> str:
 
 def evaluate_dataset(image_dir: str, truth_dir: str, names: Optional[Sequence[str]] = None, k: int = 8, iters: int = 20,
                      seed: int = 0, workers: Optional[int] = None, chunk: int = 200, want_labels: bool = False,
-                     **plan_kwargs):
+                     gpu_decode: bool = False, **plan_kwargs):
     """-> list of (name, metrics dict[, labels]) in sorted file-name order.  ``names`` (without extension)
     selects a subset.  Image i of the sorted list is clustered from initial centroids seeded with ``seed + i``.
-    ``plan_kwargs`` go to :class:`Plan` (bank, colour_space, feature, normalise, smooth ...)."""
+    ``plan_kwargs`` go to :class:`Plan` (bank, colour_space, feature, normalise, smooth ...).
+    ``gpu_decode=True`` decodes the JPEG files on the GPU (decode.decode_jpeg_batch: Huffman on host threads, inverse
+    DCT / upsampling / colour conversion as kernels; same pixels as PIL) and runs the device-resident pipeline."""
     import torch
     from PIL import Image
     files = sorted(f for f in os.listdir(image_dir) if f.lower().endswith(IMAGE_EXT))
@@ -69,12 +71,18 @@ def evaluate_dataset(image_dir: str, truth_dir: str, names: Optional[Sequence[st
             imgs_np, gts_np = imgs.numpy(), gts.numpy().view(np.uint16)
             n_gt = np.zeros(n, np.int32)
 
+            blobs = [None] * n
+
             def load(slot_i):
                 slot, i = slot_i
-                a = np.asarray(Image.open(os.path.join(image_dir, files[i])).convert("RGB"))          # script.py:25
-                if a.shape != (H, W, 3):
-                    raise ValueError("%s: decoded shape %s differs from its header" % (files[i], a.shape))
-                imgs_np[slot] = a
+                if gpu_decode:
+                    with open(os.path.join(image_dir, files[i]), "rb") as fh:
+                        blobs[slot] = fh.read()
+                else:
+                    a = np.asarray(Image.open(os.path.join(image_dir, files[i])).convert("RGB"))      # script.py:25
+                    if a.shape != (H, W, 3):
+                        raise ValueError("%s: decoded shape %s differs from its header" % (files[i], a.shape))
+                    imgs_np[slot] = a
                 for g, sgm in enumerate(segs[i]):
                     sgm = np.asarray(sgm)
                     if sgm.shape != (H, W):
@@ -84,7 +92,22 @@ def evaluate_dataset(image_dir: str, truth_dir: str, names: Optional[Sequence[st
             list(ex.map(load, enumerate(idxs)))
             plan = Plan(H, W, max_batch=min(n, chunk), k=k, iters=iters, max_gt=G, n_lab_cap=max(64, n_lab), **plan_kwargs)
             init = init_indices_for(idxs, H * W, k, seed)
-            c = plan.pipeline_host(imgs, gts, torch.from_numpy(init), n, n_gt, want_labels=want_labels)
+            if gpu_decode:
+                from .decode import decode_jpeg_batch
+                from .engine import BatchCounts
+                parts = []
+                for a in range(0, n, plan.max_batch):          # device-resident chunks of the plan's capacity
+                    b = min(n, a + plan.max_batch)
+                    d_img = decode_jpeg_batch(blobs[a:b])
+                    plan.pipeline_device(d_img, gts[a:b].cuda(non_blocking=True), torch.from_numpy(init[a:b]),
+                                         torch.from_numpy(n_gt[a:b]))
+                    parts.append(plan.fetch(want_labels=want_labels))
+                c = parts[0] if len(parts) == 1 else BatchCounts(
+                    H, W, *[np.concatenate([getattr(p_, f) for p_ in parts]) for f in
+                            ("bd_count", "gt_counts", "area", "perim", "n_seg", "n_lab", "status", "n_gt")],
+                    None, np.concatenate([p_.labels for p_ in parts]) if want_labels else None)
+            else:
+                c = plan.pipeline_host(imgs, gts, torch.from_numpy(init), n, n_gt, want_labels=want_labels)
             for slot, i in enumerate(idxs):
                 m = finish_image(c, slot)
                 out[i] = (stems[i], m, c.labels[slot].copy()) if want_labels else (stems[i], m)

@@ -207,6 +207,21 @@ GCIS_API int32_t gcis_pipeline_host(gcis_plan *plan, const uint8_t *h_img, const
                            int64_t *h_bd_count, int64_t *h_gt_counts, int32_t *h_area,
                            int32_t *h_perim, int32_t *h_n_lab, int32_t *h_status, int32_t *h_labels);
 
+/* ---- image decode (BSD_metrics/script.py:25, `img = imread(...)`) ----
+ * Baseline / extended-sequential 8-bit Huffman JPEG with 1 or 3 components (luma sampling 1x1, 2x1 or 2x2) ->
+ * the pixels libjpeg's defaults produce (islow inverse DCT, fancy upsampling, fixed-point YCbCr -> RGB), bit for
+ * bit.  Entropy decoding runs on host threads, everything after it on the GPU.  Other JPEG flavours are
+ * rejected with GCIS_E_INVALID (decode them on the host as before). */
+GCIS_API int32_t gcis_jpeg_info(const uint8_t *data, int64_t size, int32_t *h, int32_t *w, int32_t *components);
+/* quantised coefficients of one file, per component [blocks_h][blocks_w][64] in natural order (host only; used by the
+ * tests to check the device stages in isolation); returns the count or a negative error */
+GCIS_API int64_t gcis_jpeg_coefficients(const uint8_t *data, int64_t size, int16_t *coef, int64_t cap);
+/* files[i], sizes[i]: B files of one frame size H x W in host memory; d_rgb [B][H][W][3] uint8 on the device, the
+ * layout gcis_segment_device / gcis_pipeline_device take.  n_threads <= 0: one host thread per hardware thread.
+ * Returns after `stream` has finished. */
+GCIS_API int32_t gcis_jpeg_decode_batch(const uint8_t *const *files, const int64_t *sizes, int32_t B, int32_t H,
+                                        int32_t W, uint8_t *d_rgb, int32_t n_threads, void *stream);
+
 /* Stage timings (ms, CUDA events on the plan's stream) of the last
  * gcis_pipeline_device call when profiling is enabled: [colour, gabor, kmeans, metrics]. */
 GCIS_API int32_t gcis_plan_set_profiling(gcis_plan *plan, int32_t on);

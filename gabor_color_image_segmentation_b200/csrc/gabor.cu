@@ -188,6 +188,7 @@ __device__ long long gb_trace_buf[GB_TR_CTAS][8];
 #define GB_TR_ADD(slot) do { } while (0)
 #endif
 
+template <bool STATS>
 __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_constant__ GaborParams P)
 {
     extern __shared__ __align__(16) float smem[];
@@ -325,12 +326,9 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
         float *f0 = featb + (size_t)(d0 + job.out0) * P.feat_plane_stride;
         float *f1 = job.out1 >= 0 ? featb + (size_t)(d0 + job.out1) * P.feat_plane_stride : nullptr;
         const bool cx = job.row_im >= 0, ct = job.col_im >= 0;
-        long long *st0 = P.stats ? P.stats + ((size_t)b * D + d0 + job.out0) * GB_STAT_SLOTS : nullptr;
-        long long *st1 = P.stats && job.out1 >= 0 ? P.stats + ((size_t)b * D + d0 + job.out1) * GB_STAT_SLOTS : nullptr;
-        if (cx && ct) col_pass<true, true>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1, GB_WARPS, st0, st1);
-        else if (cx) col_pass<true, false>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1, GB_WARPS, st0, st1);
-        else if (ct) col_pass<false, true>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1, GB_WARPS, st0, st1);
-        else col_pass<false, false>(P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1, GB_WARPS, st0, st1);
+        long long *st0 = STATS ? P.stats + ((size_t)b * D + d0 + job.out0) * GB_STAT_SLOTS : nullptr;
+        long long *st1 = STATS && job.out1 >= 0 ? P.stats + ((size_t)b * D + d0 + job.out1) * GB_STAT_SLOTS : nullptr;
+        col_pass_dispatch<STATS>(cx, ct, P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1, GB_WARPS, st0, st1);
         GB_TR_ADD(3);
     }
 #ifdef GB_TRACE
@@ -452,10 +450,12 @@ int gabor_launch(GaborLaunchPlan &lp, const float *d_planes, float *d_feat, cons
     static SmemAttrCache attr_cache;
     size_t &attr_smem = attr_cache.cur();
     if (lp.smem > attr_smem) {
-        GCIS_CUDA_TRY(cudaFuncSetAttribute(gabor_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        GCIS_CUDA_TRY(cudaFuncSetAttribute(gabor_bank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        GCIS_CUDA_TRY(cudaFuncSetAttribute(gabor_bank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
         attr_smem = lp.smem;
     }
-    gabor_bank_kernel<<<acc, GB_THREADS, lp.smem, st>>>(p);
+    if (d_stats) gabor_bank_kernel<true><<<acc, GB_THREADS, lp.smem, st>>>(p);
+    else gabor_bank_kernel<false><<<acc, GB_THREADS, lp.smem, st>>>(p);
     GCIS_LAUNCH_CHECK();
     return GCIS_OK;
 }

@@ -311,7 +311,7 @@ __device__ __forceinline__ float fast_sqrt(float x)
 }
 
 // Column pass: lane = column of the strip, warp = blocks of GB_RC output rows.
-template <bool CX, bool CT>
+template <bool CX, bool CT, bool STATS = false>
 __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, const int *rowtab, const float *w0,
                                          int nblk, int y0, int th, int x0, float *feat0, float *feat1, int nwarps = GB_WARPS,
                                          long long *st0 = nullptr, long long *st1 = nullptr)
@@ -353,18 +353,18 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
                 const size_t o = (size_t)(y0 + r) * P.W + x0 + lane;
                 const float v0 = P.feature == GCIS_FEATURE_MAGNITUDE ? fast_sqrt(e0) : e0;
                 feat0[o] = v0;
-                if (st0) stat_add(v0, m1[0], m2[0]);
+                if constexpr (STATS) stat_add(v0, m1[0], m2[0]);
                 if (feat1) {
                     const float re1 = A + Bv, im1 = Dv - Cv;
                     const float e1 = fmaf(re1, re1, im1 * im1);
                     const float v1 = P.feature == GCIS_FEATURE_MAGNITUDE ? fast_sqrt(e1) : e1;
                     feat1[o] = v1;
-                    if (st1) stat_add(v1, m1[1], m2[1]);
+                    if constexpr (STATS) if (st1) stat_add(v1, m1[1], m2[1]);
                 }
             }
         }
     }
-    if (st0) {   // warp-shuffle reduction, then one atomic per warp, plane and moment (integers: order-independent)
+    if constexpr (STATS) {   // warp-shuffle reduction, then one atomic per warp, plane and moment (integers: order-independent)
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl) {
             long long *dst = pl ? st1 : st0;
@@ -372,6 +372,21 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
             stat_flush(dst, m1[pl], m2[pl], lane);
         }
     }
+}
+
+// run-time (CX, CT) -> compile-time instantiation; STATS (the moments of the normalisation) is a property of the whole
+// kernel, so that the kernel without it carries none of its registers
+template <bool STATS>
+__device__ __forceinline__ void col_pass_dispatch(bool cx, bool ct, const GaborParams &P, const float2 *T, const int *rowtab,
+                                                  const float *w0, int nblk, int y0, int th, int x0, float *f0, float *f1,
+                                                  int nwarps, long long *st0, long long *st1)
+{
+#define GB_COL(CXV, CTV) col_pass<CXV, CTV, STATS>(P, T, rowtab, w0, nblk, y0, th, x0, f0, f1, nwarps, st0, st1)
+    if (cx && ct) GB_COL(true, true);
+    else if (cx) GB_COL(true, false);
+    else if (ct) GB_COL(false, true);
+    else GB_COL(false, false);
+#undef GB_COL
 }
 
 // Block-0 window of a filter that stage_taps() already copied to `dst` (same arithmetic as its return value).

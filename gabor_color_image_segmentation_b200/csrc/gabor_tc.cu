@@ -191,6 +191,7 @@ __device__ __forceinline__ TcItem tc_decode(const TcParams &Q, int item)
 // Persistent kernel: one CTA per SM walks the work items i = blockIdx.x, blockIdx.x + gridDim.x, ...; the
 // orientation jobs of consecutive items form one stream through the TMA ring and the two TMEM accumulators,
 // so the tensor cores already work on the next item while the column warps finish the current one.
+template <bool STATS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUtensorMap map_plane,
                 const __grid_constant__ CUtensorMap map_table)
@@ -339,12 +340,9 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
                 float *f1 = job.out1 >= 0 ? featb + (size_t)(d0 + job.out1) * P.feat_plane_stride : nullptr;
                 const int *rt = rowtab + (w.hmax - h);
                 const bool cx = job.row_im >= 0, ct = job.col_im >= 0;
-                long long *st0 = P.stats ? P.stats + ((size_t)w.b * D + d0 + job.out0) * GB_STAT_SLOTS : nullptr;
-                long long *st1 = P.stats && job.out1 >= 0 ? P.stats + ((size_t)w.b * D + d0 + job.out1) * GB_STAT_SLOTS : nullptr;
-                if (cx && ct) col_pass<true, true>(P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW, st0, st1);
-                else if (cx) col_pass<true, false>(P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW, st0, st1);
-                else if (ct) col_pass<false, true>(P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW, st0, st1);
-                else col_pass<false, false>(P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW, st0, st1);
+                long long *st0 = STATS ? P.stats + ((size_t)w.b * D + d0 + job.out0) * GB_STAT_SLOTS : nullptr;
+                long long *st1 = STATS && job.out1 >= 0 ? P.stats + ((size_t)w.b * D + d0 + job.out1) * GB_STAT_SLOTS : nullptr;
+                col_pass_dispatch<STATS>(cx, ct, P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW, st0, st1);
                 TC_TR_ADD(3);
                 named_bar_sync(1, TC_COLT);                                          // T may be overwritten
                 TC_TR_ADD(5);
@@ -560,7 +558,8 @@ int gabor_tc_launch(GaborTcPlan &tp, const void *d_planes16, float *d_feat, cons
     static SmemAttrCache attr_cache;
     size_t &attr_smem = attr_cache.cur();
     if (tp.smem > attr_smem) {
-        GCIS_CUDA_TRY(cudaFuncSetAttribute(gabor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem));
+        GCIS_CUDA_TRY(cudaFuncSetAttribute(gabor_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem));
+        GCIS_CUDA_TRY(cudaFuncSetAttribute(gabor_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem));
         attr_smem = tp.smem;
     }
     static const int n_sm = [] {
@@ -573,7 +572,8 @@ int gabor_tc_launch(GaborTcPlan &tp, const void *d_planes16, float *d_feat, cons
     // the previous image group that the second lane runs concurrently (plan.cu)
     static const int sm_cap = [] { const char *e = getenv("GCIS_GABOR_SMS"); return e ? atoi(e) : 0; }();
     const int grid = std::min(acc, sm_cap > 0 ? std::min(sm_cap, n_sm) : n_sm);
-    gabor_tc_kernel<<<grid, TC_THREADS, tp.smem, st>>>(tp.q, map_plane, tp.map_table);
+    if (d_stats) gabor_tc_kernel<true><<<grid, TC_THREADS, tp.smem, st>>>(tp.q, map_plane, tp.map_table);
+    else gabor_tc_kernel<false><<<grid, TC_THREADS, tp.smem, st>>>(tp.q, map_plane, tp.map_table);
     GCIS_LAUNCH_CHECK();
     return GCIS_OK;
 }

@@ -11,12 +11,12 @@ no CPU fallback."""
 from .groundtruth import get_segmentation, get_segment_from_filename, pack_ground_truths
 from .metrics import metrics, finish_image, find_boundaries
 from .engine import GaborBank, Plan, BatchCounts, kmeans_init_indices, label_counts_host
-from .segment import gabor_kmeans_segment
+from .segment import gabor_kmeans_segment, slic
 from .region_scores import region_scores
 from .dataset import evaluate_dataset, print_like_script
 from .decode import decode_jpeg_batch, imread_gpu, jpeg_info
 
-__all__ = ["metrics", "get_segmentation", "get_segment_from_filename", "gabor_kmeans_segment",
+__all__ = ["metrics", "get_segmentation", "get_segment_from_filename", "gabor_kmeans_segment", "slic",
            "GaborBank", "Plan", "BatchCounts", "kmeans_init_indices", "label_counts_host",
            "pack_ground_truths", "finish_image", "find_boundaries", "region_scores",
            "evaluate_dataset", "print_like_script", "decode_jpeg_batch", "imread_gpu", "jpeg_info"]

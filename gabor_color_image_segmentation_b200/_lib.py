@@ -9,7 +9,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GCIS_LIB") or os.path.join(_PKG, "libgcis.so")
 CSRC = os.path.join(_PKG, "csrc")
-SOURCES = ["plan.cu", "gabor.cu", "gabor_tc.cu", "features.cu", "kmeans.cu", "label_metrics.cu", "jpeg.cu"]
+SOURCES = ["plan.cu", "gabor.cu", "gabor_tc.cu", "features.cu", "kmeans.cu", "label_metrics.cu", "jpeg.cu", "slic.cu"]
 
 GT_SLOTS = 8
 COLOUR = {"rgb": 0, "opponent": 1, "lab": 2}
@@ -85,6 +85,7 @@ SIGNATURES = {
     "gcis_jpeg_info": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "gcis_jpeg_coefficients": (_i64, [_vp, _i64, _vp, _i64]),
     "gcis_jpeg_decode_batch": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "gcis_slic_host": (_i32, [_vp, _i32, _i32, _i32, C.c_double, _i32, _i32, _i32, _vp]),
     "gcis_plan_set_profiling": (_i32, [_vp, _i32]),
     "gcis_plan_last_stage_ms": (_i32, [_vp, _vp]),
 }

@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from . import _lib
 from .engine import GaborBank, Plan, kmeans_init_indices
 
 _PLANS = {}
@@ -36,3 +37,19 @@ def gabor_kmeans_segment(img, n_clusters=8, n_iter=20, seed=0, bank: GaborBank =
     d_img = torch.from_numpy(img).cuda()[None]
     labels = plan.segment(d_img, torch.from_numpy(np.asarray(init_idx, np.int32))[None])
     return labels[0].cpu().numpy()
+
+
+def slic(image, n_segments=100, compactness=10.0, max_num_iter=10, enforce_connectivity=True, start_label=1):
+    """Stand-in for ``skimage.segmentation.slic`` at BSD_metrics/script.py:11,30 (same name, same leading keywords and
+    defaults): H x W x 3 uint8 -> H x W integer labels from ``start_label``.  scikit-image's published algorithm
+    (float64 CIELAB, regular-grid seeds, ``max_num_iter`` assignment / update rounds, connectivity enforcement) on the
+    GPU; parity with a given scikit-image release is unpinned.  Options this build does not have
+    (sigma, spacing, masks, slic_zero, non-RGB input) are not accepted."""
+    img = np.ascontiguousarray(image)
+    if img.ndim != 3 or img.shape[2] != 3 or img.dtype != np.uint8:
+        raise ValueError("image must be H x W x 3 uint8")
+    H, W = img.shape[:2]
+    labels = np.empty((H, W), np.int32)
+    _lib.check(_lib.load().gcis_slic_host(img.ctypes.data, H, W, int(n_segments), float(compactness), int(max_num_iter),
+                                          int(bool(enforce_connectivity)), int(start_label), labels.ctypes.data), "gcis_slic_host")
+    return labels

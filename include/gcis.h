@@ -222,6 +222,14 @@ GCIS_API int64_t gcis_jpeg_coefficients(const uint8_t *data, int64_t size, int16
 GCIS_API int32_t gcis_jpeg_decode_batch(const uint8_t *const *files, const int64_t *sizes, int32_t B, int32_t H,
                                         int32_t W, uint8_t *d_rgb, int32_t n_threads, void *stream);
 
+/* ---- SLIC superpixels: the segmenter the reference itself calls (BSD_metrics/script.py:11,30:
+ * skimage.segmentation.slic(img, n_segments=300, compactness=10.0)).  scikit-image's published algorithm in float64
+ * (third-party and unpinned upstream: parity unpinned).  One H x W x 3 uint8 image in host memory ->
+ * h_labels [H][W] int32; assignment and centroid update run on the GPU, the connectivity pass on the host.
+ * Returns the number of seeds or a negative error. */
+GCIS_API int32_t gcis_slic_host(const uint8_t *h_img, int32_t H, int32_t W, int32_t n_segments, double compactness,
+                                int32_t max_iter, int32_t enforce_connectivity, int32_t start_label, int32_t *h_labels);
+
 /* Stage timings (ms, CUDA events on the plan's stream) of the last
  * gcis_pipeline_device call when profiling is enabled: [colour, gabor, kmeans, metrics]. */
 GCIS_API int32_t gcis_plan_set_profiling(gcis_plan *plan, int32_t on);

@@ -434,3 +434,179 @@ ORC_API void orc_kmeans_assign_f64(const float *feat, int D, int64_t N, int k,
         labels[p] = bj; best_d2[p] = b1; second_d2[p] = b2;
     }
 }
+
+/* ------------------------------------------------------------------------- */
+/* SLIC superpixels (the segmenter the reference actually calls,               */
+/* BSD_metrics/script.py:11,30: skimage.segmentation.slic(img, n_segments=300, */
+/* compactness=10.0)).  scikit-image is third-party, un-vendored, unpinned and */
+/* absent from this image, so this follows its published algorithm             */
+/* (slic_superpixels.py / _slic.pyx, 0.19 line) as restated in DESIGN.md 3.8:  */
+/* PARITY UNPINNED.  float64 throughout, like scikit-image.                    */
+/* ------------------------------------------------------------------------- */
+
+/* cube root with IEEE operations only (bit-identical on the CPU and in the CUDA kernel; not correctly rounded):
+ * frexp-style range reduction to [1/8, 1), a quadratic seed and five Newton steps y <- y - (y^3 - t) / (3 y^2) */
+ORC_API double orc_det_cbrt(double t)
+{
+    if (t <= 0.0) return 0.0;
+    int e = 0;
+    double m = t;
+    while (m >= 1.0) { m *= 0.125; e += 1; }
+    while (m < 0.125) { m *= 8.0; e -= 1; }
+    double y = 0.4928 + m * (0.8203 - m * 0.3131);         /* rough fit of cbrt on [1/8, 1) */
+    for (int i = 0; i < 5; ++i) {
+        double y2 = y * y;
+        double num = y2 * y - m;
+        double den = 3.0 * y2;
+        y = y - num / den;
+    }
+    while (e > 0) { y *= 2.0; e -= 1; }
+    while (e < 0) { y *= 0.5; e += 1; }
+    return y;
+}
+
+/* skimage.color.rgb2lab (D65, 2 degree observer) of one 8-bit pixel, channels scaled by `ratio` = 1 / compactness */
+static void slic_lab(const double *lin, const uint8_t *px, double ratio, double *out)
+{
+    const double r = lin[px[0]], g = lin[px[1]], b = lin[px[2]];
+    double x = (0.412453 * r + 0.357580 * g) + 0.180423 * b;
+    double y = (0.212671 * r + 0.715160 * g) + 0.072169 * b;
+    double z = (0.019334 * r + 0.119193 * g) + 0.950227 * b;
+    x = x / 0.95047; z = z / 1.08883;
+    const double fx = x > 0.008856 ? orc_det_cbrt(x) : 7.787 * x + 16.0 / 116.0;
+    const double fy = y > 0.008856 ? orc_det_cbrt(y) : 7.787 * y + 16.0 / 116.0;
+    const double fz = z > 0.008856 ? orc_det_cbrt(z) : 7.787 * z + 16.0 / 116.0;
+    out[0] = (116.0 * fy - 16.0) * ratio;
+    out[1] = (500.0 * (fx - fy)) * ratio;
+    out[2] = (200.0 * (fy - fz)) * ratio;
+}
+
+/* skimage.util.regular_grid for a (1, H, W) volume: start and step along y and x */
+ORC_API void orc_slic_grid(int H, int W, int n_points, int *start_y, int *step_y, int *start_x, int *step_x)
+{
+    const double space = (double)H * (double)W;
+    if (space <= (double)n_points) { *start_y = *start_x = 0; *step_y = *step_x = 1; return; }
+    /* sorted dims (1, min, max): the unit depth axis is absorbed first, the other two share sqrt(space / n) */
+    double s = sqrt(space / (double)n_points);
+    const int lo = H < W ? H : W, hi = H < W ? W : H;
+    double s_lo = s, s_hi = s;
+    if ((double)lo < s) { s_lo = (double)lo; s_hi = (double)hi / (double)n_points; }
+    const double sy = H < W ? s_lo : s_hi, sx = H < W ? s_hi : s_lo;
+    const double use_y = (H == W) ? s : sy, use_x = (H == W) ? s : sx;
+    *start_y = (int)floor(use_y / 2.0); *start_x = (int)floor(use_x / 2.0);
+    *step_y = (int)nearbyint(use_y); *step_x = (int)nearbyint(use_x);
+    if (*step_y < 1) *step_y = 1;
+    if (*step_x < 1) *step_x = 1;
+}
+
+/* _enforce_label_connectivity_cython: raster scan, breadth-first growth of each 4-connected component up to
+ * max_size pixels; components smaller than min_size take the label of the last adjacent, already relabelled
+ * component seen during the search; the others get consecutive new labels from start_label. */
+ORC_API void orc_slic_connectivity(const int32_t *seg, int H, int W, int min_size, int max_size, int start_label, int32_t *out)
+{
+    const int ddx[4] = {1, -1, 0, 0}, ddy[4] = {0, 0, 1, -1};
+    int32_t *cy = malloc(sizeof(int32_t) * (size_t)(max_size > 0 ? max_size : 1)), *cx = malloc(sizeof(int32_t) * (size_t)(max_size > 0 ? max_size : 1));
+    for (size_t i = 0; i < (size_t)H * W; ++i) out[i] = -1;
+    int32_t cur = start_label;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            if (out[(size_t)y * W + x] >= 0) continue;
+            int32_t adjacent = 0;
+            const int32_t label = seg[(size_t)y * W + x];
+            out[(size_t)y * W + x] = cur;
+            int size = 1, visited = 0;
+            cy[0] = y; cx[0] = x;
+            while (visited < size && size < max_size) {
+                for (int i = 0; i < 4; ++i) {
+                    const int yy = cy[visited] + ddy[i], xx = cx[visited] + ddx[i];
+                    if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
+                    const size_t q = (size_t)yy * W + xx;
+                    if (seg[q] == label && out[q] == -1) {
+                        out[q] = cur;
+                        cy[size] = yy; cx[size] = xx;
+                        size += 1;
+                        if (size >= max_size) break;
+                    } else if (out[q] >= 0 && out[q] != cur) {
+                        adjacent = out[q];
+                    }
+                }
+                visited += 1;
+            }
+            if (size < min_size) {
+                for (int i = 0; i < size; ++i) out[(size_t)cy[i] * W + cx[i]] = adjacent;
+            } else {
+                cur += 1;
+            }
+        }
+    free(cy); free(cx);
+}
+
+/* slic(img, n_segments, compactness, max_num_iter, sigma=0, convert2lab=True, enforce_connectivity, min_size_factor=0.5,
+ * max_size_factor=3, start_label): labels [H][W] int32.  lin256 = the sRGB -> linear table of the 256 channel values
+ * (computed by the caller with libm pow, so that checker and product use the very same numbers). */
+ORC_API int orc_slic(const uint8_t *img, int H, int W, int n_segments, double compactness, int max_iter,
+                     int enforce, int start_label, const double *lin256, int32_t *labels)
+{
+    const size_t N = (size_t)H * W;
+    int sy0, sy, sx0, sx;
+    orc_slic_grid(H, W, n_segments, &sy0, &sy, &sx0, &sx);
+    const int ny = (H - sy0 + sy - 1) / sy, nx = (W - sx0 + sx - 1) / sx, K = ny * nx;
+    if (K < 1) return -1;
+    const double ratio = 1.0 / compactness;
+    const int step = sy > sx ? sy : sx;
+    const double spatial_weight = 1.0 / ((double)step * (double)step);
+    double *lab = malloc(sizeof(double) * N * 3), *segs = malloc(sizeof(double) * (size_t)K * 5), *dist = malloc(sizeof(double) * N);
+    int32_t *near = calloc(N, sizeof(int32_t));
+    int64_t *cnt = malloc(sizeof(int64_t) * (size_t)K);
+    for (size_t p = 0; p < N; ++p) slic_lab(lin256, img + 3 * p, ratio, lab + 3 * p);
+    for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) {
+            double *s = segs + (size_t)(j * nx + i) * 5;
+            s[0] = (double)(sy0 + j * sy); s[1] = (double)(sx0 + i * sx); s[2] = s[3] = s[4] = 0.0;   /* colours start at zero */
+        }
+    for (int it = 0; it < max_iter; ++it) {
+        for (size_t p = 0; p < N; ++p) dist[p] = 1.7976931348623157e308;
+        for (int k = 0; k < K; ++k) {
+            const double *s = segs + (size_t)k * 5;
+            const double c_y = s[0], c_x = s[1];
+            double t;
+            t = c_y - 2.0 * sy; const long y_min = (long)(t > 0.0 ? t : 0.0);
+            t = c_y + 2.0 * sy + 1.0; const long y_max = (long)(t < (double)H ? t : (double)H);
+            t = c_x - 2.0 * sx; const long x_min = (long)(t > 0.0 ? t : 0.0);
+            t = c_x + 2.0 * sx + 1.0; const long x_max = (long)(t < (double)W ? t : (double)W);
+            for (long y = y_min; y < y_max; ++y) {
+                const double dy = (c_y - (double)y) * (c_y - (double)y);
+                for (long x = x_min; x < x_max; ++x) {
+                    const double dx = (c_x - (double)x) * (c_x - (double)x);
+                    double d = (dy + dx) * spatial_weight;
+                    const double *l = lab + 3 * ((size_t)y * W + x);
+                    double dc = 0.0;
+                    for (int c = 0; c < 3; ++c) dc += (l[c] - s[2 + c]) * (l[c] - s[2 + c]);
+                    d += dc;
+                    if (dist[(size_t)y * W + x] > d) { near[(size_t)y * W + x] = k; dist[(size_t)y * W + x] = d; }
+                }
+            }
+        }
+        memset(cnt, 0, sizeof(int64_t) * (size_t)K);
+        for (size_t i = 0; i < (size_t)K * 5; ++i) segs[i] = 0.0;
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                const size_t p = (size_t)y * W + x;
+                double *s = segs + (size_t)near[p] * 5;
+                cnt[near[p]] += 1;
+                s[0] += (double)y; s[1] += (double)x;
+                for (int c = 0; c < 3; ++c) s[2 + c] += lab[3 * p + c];
+            }
+        for (int k = 0; k < K; ++k)
+            for (int c = 0; c < 5; ++c) segs[(size_t)k * 5 + c] /= (double)cnt[k];   /* 0/0 -> NaN, like scikit-image: the segment dies */
+    }
+    if (enforce) {
+        const double segment_size = (double)N / (double)K;
+        const int min_size = (int)(0.5 * segment_size), max_size = (int)(3.0 * segment_size);
+        orc_slic_connectivity(near, H, W, min_size, max_size, start_label, labels);
+    } else {
+        for (size_t p = 0; p < N; ++p) labels[p] = near[p] + start_label;
+    }
+    free(lab); free(segs); free(dist); free(near); free(cnt);
+    return K;
+}

@@ -342,7 +342,7 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
                 const bool cx = job.row_im >= 0, ct = job.col_im >= 0;
                 long long *st0 = STATS ? P.stats + ((size_t)w.b * D + d0 + job.out0) * GB_STAT_SLOTS : nullptr;
                 long long *st1 = STATS && job.out1 >= 0 ? P.stats + ((size_t)w.b * D + d0 + job.out1) * GB_STAT_SLOTS : nullptr;
-                col_pass_dispatch<STATS>(cx, ct, P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW, st0, st1);
+                col_pass_dispatch<STATS>(cx, ct, P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW, st0, st1, h);
                 TC_TR_ADD(3);
                 named_bar_sync(1, TC_COLT);                                          // T may be overwritten
                 TC_TR_ADD(5);

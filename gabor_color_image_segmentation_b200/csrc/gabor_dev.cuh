@@ -77,9 +77,16 @@ __device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi)
 #endif
 constexpr int GB_SWEEP_UNR = GB_SWEEP_UNROLL;   // pairs of blocks per unrolled step of the sweeps
 
+//
+// The first and the last block are triangular: block 0 only reaches taps <= 2h for outputs i <= u, the last block only
+// taps >= 0 for outputs i >= u + d with d = (nblk - 1) R - 2h; the other products multiply the zero padding around the
+// taps.  With `d` >= 0 (caller guarantees 2h >= R, so no block is cut on both sides) those products are not issued:
+// 16 % fewer FMAs for the 15/29/55/109-tap bank, same sums (x * 0 added to an accumulator leaves its value).
+template <int N> struct IntC { static constexpr int value = N; };
+
 template <int R, bool CT, bool CX, class XLoad>
 __device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u64 (&P)[R], u64 (&Q)[R], float (&S)[R],
-                                      const float *xvec = nullptr)
+                                      const float *xvec = nullptr, int d = -1)
 {
     // The window of block m is taps [base - m R, base - m R + 2R): its upper half is the lower half of
     // block m - 1, so each block loads only its R new taps (the tap loads are warp-uniform shared loads
@@ -103,8 +110,11 @@ __device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u6
             }
         }
     };
-    auto block = [&](int m, const u64 (&clo)[CT ? R : 1], const u64 (&chi)[CT ? R : 1], const float (&rlo)[CT ? 1 : R],
-                     const float (&rhi)[CT ? 1 : R]) {
+    // MODE 0: all R x R products; 1: first block (outputs i <= u); 2: last block (outputs i >= u + DD)
+    auto block = [&](auto mode_c, auto dd_c, int m, const u64 (&clo)[CT ? R : 1], const u64 (&chi)[CT ? R : 1],
+                     const float (&rlo)[CT ? 1 : R], const float (&rhi)[CT ? 1 : R]) {
+        constexpr int MODE = decltype(mode_c)::value, DD = decltype(dd_c)::value;
+        constexpr int NIN = MODE == 2 ? R - DD : R;   // inputs that reach at least one output
         float xr[R], xi[R];
         u64 xp[R];
         if (R == 4 && !CX && xvec) {   // row pass: the R inputs of a block are one aligned 128-bit load
@@ -112,12 +122,14 @@ __device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u6
             xr[0] = v.x; xr[1 % R] = v.y; xr[2 % R] = v.z; xr[3 % R] = v.w;
         } else {
 #pragma unroll
-            for (int uu = 0; uu < R; ++uu) xload(m * R + uu, xr[uu], xi[uu], xp[uu]);
+            for (int uu = 0; uu < NIN; ++uu) xload(m * R + uu, xr[uu], xi[uu], xp[uu]);
         }
 #pragma unroll
-        for (int uu = 0; uu < R; ++uu) {
+        for (int uu = 0; uu < NIN; ++uu) {
 #pragma unroll
             for (int i = 0; i < R; ++i) {
+                if (MODE == 1 && i > uu) continue;
+                if (MODE == 2 && i < uu + DD) continue;
                 const int t = i - uu + R - 1;
                 if constexpr (CT) {
                     const u64 w = t < R ? clo[t % R] : chi[t % R];
@@ -131,14 +143,47 @@ __device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u6
             }
         }
     };
+    if (d >= 0) {
+        const int last = nblk - 1;
+        load_half(0, ca, ra);
+        block(IntC<1>{}, IntC<0>{}, 0, ca, ca, ra, ra);            // the upper half (padding) is never read
+        int m = 1;
+#pragma unroll 1
+        while (m < last) {
+            load_half(m, cb, rb);
+            block(IntC<0>{}, IntC<0>{}, m, cb, ca, rb, ra);
+            ++m;
+            if (m < last) {
+                load_half(m, ca, ra);
+                block(IntC<0>{}, IntC<0>{}, m, ca, cb, ra, rb);
+                ++m;
+            }
+        }
+        if (last & 1) {   // the half shared with block last - 1 sits in ca: the last block reads it from cb
+#pragma unroll
+            for (int q = 0; q < (CT ? R : 1); ++q) cb[q] = ca[q];
+#pragma unroll
+            for (int q = 0; q < (CT ? 1 : R); ++q) rb[q] = ra[q];
+        }
+        switch (d) {
+        case 2: block(IntC<2>{}, IntC<2>{}, last, ca, cb, ra, rb); break;   // d >= 1: only the shared half is reached
+        case 4: block(IntC<2>{}, IntC<4>{}, last, ca, cb, ra, rb); break;
+        case 6: block(IntC<2>{}, IntC<6 < R ? 6 : 0>{}, last, ca, cb, ra, rb); break;
+        default:                                                            // d = 0 (tap 0 of the new half) or any other
+            load_half(last, ca, ra);
+            if (d == 0) block(IntC<2>{}, IntC<0>{}, last, ca, cb, ra, rb);
+            else block(IntC<0>{}, IntC<0>{}, last, ca, cb, ra, rb);
+        }
+        return;
+    }
     load_half(-1, cb, rb);   // upper half of block 0
 #pragma unroll GB_SWEEP_UNR
     for (int m = 0; m < nblk; m += 2) {
         load_half(m, ca, ra);
-        block(m, ca, cb, ra, rb);
+        block(IntC<0>{}, IntC<0>{}, m, ca, cb, ra, rb);
         if (m + 1 < nblk) {
             load_half(m + 1, cb, rb);
-            block(m + 1, cb, ca, rb, ra);
+            block(IntC<0>{}, IntC<0>{}, m + 1, cb, ca, rb, ra);
         }
     }
 }
@@ -312,6 +357,10 @@ __device__ __forceinline__ float fast_sqrt(float x)
 
 // Column pass: lane = column of the strip, warp = blocks of GB_RC output rows.
 constexpr int GB_TAIL_MAX = 2;   // leftover rows (th mod GB_RC) up to this many get the thin single-row path
+#ifndef GB_TRI
+#define GB_TRI 1                 // triangular first/last sweep blocks (needs the registers of a <= 16-warp CTA)
+#endif
+constexpr int GB_THIN_COLS = 4;  // strips with at most this many image columns get the lanes-on-rows path
 
 template <bool CX, bool CT, bool STATS = false>
 __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, const int *rowtab, const float *w0,
@@ -325,14 +374,15 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
     // warps that own the fewest blocks.  (Dealing the rows in units of 4 so that every warp gets the same number, with
     // one 4-row block per warp, was measured slower: 36.7 vs 34.3 us per image at K = 109.)
     const int nfull = th / GB_RC, tail = th - nfull * GB_RC;
-    const bool thin_tail = h >= 0 && tail > 0 && tail <= GB_TAIL_MAX && nfull >= nwarps;
+    const bool thin_tail = h >= 0 && tail > 0 && tail <= GB_TAIL_MAX && nfull >= nwarps && P.W - x0 > GB_THIN_COLS;
     const int nrb = thin_tail ? nfull : (th + GB_RC - 1) / GB_RC;
-    const bool col_ok = x0 + lane < P.W;
     const u64 *Tl = reinterpret_cast<const u64 *>(T) + lane;
+    // triangular first/last block of the sweep when the taps span at least one block (always for the BSDS bank)
+    const int tri_d = (GB_TRI && h >= 0 && 2 * h >= GB_RC && nblk == (2 * h + 2 * GB_RC - 1) / GB_RC) ? (nblk - 1) * GB_RC - 2 * h : -1;
     int m1[2] = {0, 0};                      // exact integer moments of what this thread writes (normalisation)
     unsigned long long m2[2] = {0, 0};
-    auto emit = [&](int r, u64 Pa, u64 Qa, float Sa) {
-        if (r < th && col_ok) {
+    auto emit = [&](int r, int col, u64 Pa, u64 Qa, float Sa) {
+        if (r < th && x0 + col < P.W) {
             float A, Bv = 0.f, Cv = 0.f, Dv = 0.f;
             if constexpr (CT) {
                 unpack2(Pa, A, Dv);
@@ -345,7 +395,7 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
             // theta: (A - B) + i(C + D);  pi - theta: (A + B) + i(D - C)
             const float re0 = A - Bv, im0 = Cv + Dv;
             const float e0 = fmaf(re0, re0, im0 * im0);
-            const size_t o = (size_t)(y0 + r) * P.W + x0 + lane;
+            const size_t o = (size_t)(y0 + r) * P.W + x0 + col;
             const float v0 = P.feature == GCIS_FEATURE_MAGNITUDE ? fast_sqrt(e0) : e0;
             feat0[o] = v0;
             if constexpr (STATS) stat_add(v0, m1[0], m2[0]);
@@ -358,7 +408,50 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
             }
         }
     };
-    for (int rb = warp; rb < nrb; rb += nwarps) {
+    // One output (row r, strip column col) as a plain tap loop: the taps in the order the sweep applies them, so the
+    // same bits.  r and col may differ from lane to lane.
+    auto one_output = [&](int r, int col) {
+        const int *rt = rowtab + r;
+        const u64 *Tc = reinterpret_cast<const u64 *>(T) + col;
+        u64 Pa = 0ull, Qa = 0ull;
+        float Sa = 0.f;
+        if constexpr (CT) {
+            const u64 *tp = reinterpret_cast<const u64 *>(w0 - 2 * (2 * h + 1 - GB_RC));   // complex tap 0
+#pragma unroll 4
+            for (int u = 0; u <= 2 * h; ++u) {
+                float xr, xi;
+                unpack2(Tc[rt[u]], xr, xi);
+                const u64 w = tp[2 * h - u];
+                fma2_vs(Pa, w, xr);
+                if constexpr (CX) fma2_vs(Qa, w, xi);
+            }
+        } else {
+            const float *tp = w0 - (2 * h - GB_RC + 1);                                      // real tap 0
+#pragma unroll 4
+            for (int u = 0; u <= 2 * h; ++u) {
+                const u64 xp = Tc[rt[u]];
+                const float w = tp[2 * h - u];
+                if constexpr (CX) {
+                    fma2_vs(Pa, xp, w);
+                } else {
+                    float xr, xi;
+                    unpack2(xp, xr, xi);
+                    Sa = fmaf(w, xr, Sa);
+                }
+            }
+        }
+        emit(r, col, Pa, Qa, Sa);
+    };
+    // 481 and 321 columns are whole 32-column strips + ONE column: the last strip would run the full register-blocked
+    // sweep for 1 useful lane in 32 (6 % / 9 % of the whole column pass).  A strip of at most GB_THIN_COLS columns
+    // instead puts the lanes on ROWS, one output per lane and pass.
+    const int ncols = min(GB_TW, P.W - x0);
+    const bool thin_strip = h >= 0 && ncols <= GB_THIN_COLS;
+    if (thin_strip) {
+        for (int c = 0; c < ncols; ++c)
+            for (int r = warp * 32 + lane; r < th; r += nwarps * 32) one_output(r, c);
+    }
+    for (int rb = warp; rb < (thin_strip ? 0 : nrb); rb += nwarps) {
         u64 Pv[GB_RC], Qv[GB_RC];
         float Sv[GB_RC];
 #pragma unroll
@@ -369,45 +462,13 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
                 xp = Tl[rt[u]];
                 unpack2(xp, xr, xi);
             },
-            w0, nblk, Pv, Qv, Sv);
+            w0, nblk, Pv, Qv, Sv, nullptr, tri_d);
 #pragma unroll
-        for (int i = 0; i < GB_RC; ++i) emit(rb * GB_RC + i, Pv[i], Qv[i], Sv[i]);
+        for (int i = 0; i < GB_RC; ++i) emit(rb * GB_RC + i, lane, Pv[i], Qv[i], Sv[i]);
     }
-    if (thin_tail) {
-        for (int tr = 0; tr < tail; ++tr) {
-            if (warp != nwarps - 1 - tr) continue;
-            const int r = nfull * GB_RC + tr;
-            const int *rt = rowtab + r;
-            u64 Pa = 0ull, Qa = 0ull;
-            float Sa = 0.f;
-            if constexpr (CT) {
-                const u64 *tp = reinterpret_cast<const u64 *>(w0 - 2 * (2 * h + 1 - GB_RC));   // complex tap 0
-#pragma unroll 4
-                for (int u = 0; u <= 2 * h; ++u) {
-                    float xr, xi;
-                    unpack2(Tl[rt[u]], xr, xi);
-                    const u64 w = tp[2 * h - u];
-                    fma2_vs(Pa, w, xr);
-                    if constexpr (CX) fma2_vs(Qa, w, xi);
-                }
-            } else {
-                const float *tp = w0 - (2 * h - GB_RC + 1);                                      // real tap 0
-#pragma unroll 4
-                for (int u = 0; u <= 2 * h; ++u) {
-                    const u64 xp = Tl[rt[u]];
-                    const float w = tp[2 * h - u];
-                    if constexpr (CX) {
-                        fma2_vs(Pa, xp, w);
-                    } else {
-                        float xr, xi;
-                        unpack2(xp, xr, xi);
-                        Sa = fmaf(w, xr, Sa);
-                    }
-                }
-            }
-            emit(r, Pa, Qa, Sa);
-        }
-    }
+    if (thin_tail)
+        for (int tr = 0; tr < tail; ++tr)
+            if (warp == nwarps - 1 - tr) one_output(nfull * GB_RC + tr, lane);
     if constexpr (STATS) {   // warp-shuffle reduction, then one atomic per warp, plane and moment (integers: order-independent)
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl) {

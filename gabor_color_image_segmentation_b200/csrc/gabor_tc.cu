@@ -43,9 +43,11 @@ using namespace gbdev;
 namespace {
 
 #ifndef TC_COLW_N
-#define TC_COLW_N 16
+#define TC_COLW_N 12
 #endif
-constexpr int TC_COLW = TC_COLW_N;             // column-pass warps: 4 per SM sub-partition
+constexpr int TC_COLW = TC_COLW_N;             // column-pass warps: 3 per SM sub-partition; with the two issuing warps the CTA is 14
+                                               // warps, at most 4 per sub-partition = 128 registers per thread (18 warps: 96, and
+                                               // the triangular sweep of gabor_dev.cuh spills: 16 warps 94.7, 12 warps 71.6 us/image)
 constexpr int TC_COLT = TC_COLW * 32;
 constexpr int TC_TMA_WARP = TC_COLW, TC_MMA_WARP = TC_COLW + 1;
 constexpr int TC_THREADS = TC_COLT + 64;
@@ -165,8 +167,19 @@ __device__ __forceinline__ TcItem tc_decode(const TcParams &Q, int item)
     it.s = P.order[range];
     int rem = item - P.first_block[range];
     const int nvt = P.n_vt[it.s];
-    const int vt = rem % nvt; rem /= nvt;
-    const int strip = rem % P.n_strips; rem /= P.n_strips;
+    // A last strip of a few columns (481 = 15 x 32 + 1) costs the column warps ~5 % of a full one (col_pass's lanes-on-
+    // rows path): those items come LAST in the scale's range, so the round-robin deal gives every CTA its share of them.
+    const int thin = (P.n_strips > 1 && P.W - (P.n_strips - 1) * GB_TW <= gbdev::GB_THIN_COLS) ? 1 : 0;
+    const int nfat = P.n_strips - thin, n_fat_items = P.B * P.C * nfat * nvt;
+    int strip;
+    const int vt = rem % nvt;
+    if (rem < n_fat_items) {
+        rem /= nvt;
+        strip = rem % nfat; rem /= nfat;
+    } else {
+        rem = (rem - n_fat_items) / nvt;
+        strip = P.n_strips - 1;
+    }
     it.c = rem % P.C;
     it.b = rem / P.C;
     it.x0 = strip * GB_TW;

@@ -28,6 +28,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
 }
+// The same wait for a thread that may wait long beside busy warps (the issuing threads of a warp-specialised kernel):
+// try_wait with a suspend-time hint parks the thread in hardware instead of polling every ~13 cycles, so the loop does
+// not take issue slots from the warps that share its SM sub-partition.
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+    } while (!ok);
+}
 // global -> shared bulk copy; completion is signalled on `bar` as transferred bytes
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {

@@ -381,31 +381,66 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
     const int tri_d = (GB_TRI && h >= 0 && 2 * h >= GB_RC && nblk == (2 * h + 2 * GB_RC - 1) / GB_RC) ? (nblk - 1) * GB_RC - 2 * h : -1;
     int m1[2] = {0, 0};                      // exact integer moments of what this thread writes (normalisation)
     unsigned long long m2[2] = {0, 0};
-    auto emit = [&](int r, int col, u64 Pa, u64 Qa, float Sa) {
+    const bool mag = P.feature == GCIS_FEATURE_MAGNITUDE, pair = feat1 != nullptr;
+    // accumulators of one output -> the feature value(s): theta: (A - B) + i(C + D);  pi - theta: (A + B) + i(D - C)
+    auto values = [&](u64 Pa, u64 Qa, float Sa, float &v0, float &v1) {
+        float A, Bv = 0.f, Cv = 0.f, Dv = 0.f;
+        if constexpr (CT) {
+            unpack2(Pa, A, Dv);
+            if constexpr (CX) unpack2(Qa, Cv, Bv);
+        } else if constexpr (CX) {
+            unpack2(Pa, A, Cv);
+        } else {
+            A = Sa;
+        }
+        const float re0 = A - Bv, im0 = Cv + Dv;
+        const float e0 = fmaf(re0, re0, im0 * im0);
+        v0 = mag ? fast_sqrt(e0) : e0;
+        v1 = 0.f;
+        if (pair) {
+            const float re1 = A + Bv, im1 = Dv - Cv;
+            const float e1 = fmaf(re1, re1, im1 * im1);
+            v1 = mag ? fast_sqrt(e1) : e1;
+        }
+    };
+    auto store = [&](float *o0, float *o1, float v0, float v1) {
+        *o0 = v0;
+        if constexpr (STATS) stat_add(v0, m1[0], m2[0]);
+        if (pair) {
+            *o1 = v1;
+            if constexpr (STATS) if (st1) stat_add(v1, m1[1], m2[1]);
+        }
+    };
+    auto emit = [&](int r, int col, u64 Pa, u64 Qa, float Sa) {   // one output of the thin paths
         if (r < th && x0 + col < P.W) {
-            float A, Bv = 0.f, Cv = 0.f, Dv = 0.f;
-            if constexpr (CT) {
-                unpack2(Pa, A, Dv);
-                if constexpr (CX) unpack2(Qa, Cv, Bv);
-            } else if constexpr (CX) {
-                unpack2(Pa, A, Cv);
-            } else {
-                A = Sa;
-            }
-            // theta: (A - B) + i(C + D);  pi - theta: (A + B) + i(D - C)
-            const float re0 = A - Bv, im0 = Cv + Dv;
-            const float e0 = fmaf(re0, re0, im0 * im0);
+            float v0, v1;
+            values(Pa, Qa, Sa, v0, v1);
             const size_t o = (size_t)(y0 + r) * P.W + x0 + col;
-            const float v0 = P.feature == GCIS_FEATURE_MAGNITUDE ? fast_sqrt(e0) : e0;
-            feat0[o] = v0;
-            if constexpr (STATS) stat_add(v0, m1[0], m2[0]);
-            if (feat1) {
-                const float re1 = A + Bv, im1 = Dv - Cv;
-                const float e1 = fmaf(re1, re1, im1 * im1);
-                const float v1 = P.feature == GCIS_FEATURE_MAGNITUDE ? fast_sqrt(e1) : e1;
-                feat1[o] = v1;
-                if constexpr (STATS) if (st1) stat_add(v1, m1[1], m2[1]);
+            store(feat0 + o, feat1 + o, v0, v1);
+        }
+    };
+    // the GB_RC rows of a block: one pointer per plane stepping by the image width, no per-row index arithmetic; whole
+    // blocks (all but a masked last one) without per-row tests (the column pass is issue bound: see profiles/)
+    auto emit_block = [&](int r0, const u64 (&Pv)[GB_RC], const u64 (&Qv)[GB_RC], const float (&Sv)[GB_RC]) {
+        if (x0 + lane >= P.W) return;
+        const size_t o = (size_t)(y0 + r0) * P.W + x0 + lane;
+        float *o0 = feat0 + o, *o1 = feat1 + o;
+        const int nrow = th - r0;
+        if (nrow >= GB_RC) {
+#pragma unroll
+            for (int i = 0; i < GB_RC; ++i, o0 += P.W, o1 += P.W) {
+                float v0, v1;
+                values(Pv[i], Qv[i], Sv[i], v0, v1);
+                store(o0, o1, v0, v1);
             }
+        } else {
+#pragma unroll
+            for (int i = 0; i < GB_RC; ++i, o0 += P.W, o1 += P.W)
+                if (i < nrow) {
+                    float v0, v1;
+                    values(Pv[i], Qv[i], Sv[i], v0, v1);
+                    store(o0, o1, v0, v1);
+                }
         }
     };
     // One output (row r, strip column col) as a plain tap loop: the taps in the order the sweep applies them, so the
@@ -463,8 +498,7 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
                 unpack2(xp, xr, xi);
             },
             w0, nblk, Pv, Qv, Sv, nullptr, tri_d);
-#pragma unroll
-        for (int i = 0; i < GB_RC; ++i) emit(rb * GB_RC + i, lane, Pv[i], Qv[i], Sv[i]);
+        emit_block(rb * GB_RC, Pv, Qv, Sv);
     }
     if (thin_tail)
         for (int tr = 0; tr < tail; ++tr)

@@ -252,7 +252,7 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
                     for (int rb = 0; rb < w.n_rb; ++rb)
                         for (int a = 0; a < w.n_atoms; ++a, ++it) {
                             const int st = it % TC_STAGES;
-                            mbar_wait(smem_u32(&s_empty[st]), ((it / TC_STAGES) & 1) ^ 1);
+                            mbar_wait_parked(smem_u32(&s_empty[st]), ((it / TC_STAGES) & 1) ^ 1);
                             const uint32_t fb = smem_u32(&s_full[st]);
                             const uint32_t dst = ring + st * TC_STAGE_BYTES;
                             mbar_expect_tx(fb, TC_STAGE_BYTES);
@@ -272,13 +272,13 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
                 const TcItem w = tc_decode(Q, item);
                 for (int ji = 0; ji < w.n_jobs; ++ji, ++jg) {
                     const int buf = jg & 1;
-                    mbar_wait(smem_u32(&s_tempty[buf]), ((jg >> 1) & 1) ^ 1);    // accumulator drained by the column warps
+                    mbar_wait_parked(smem_u32(&s_tempty[buf]), ((jg >> 1) & 1) ^ 1);    // accumulator drained by the column warps
                     tc_fence_after();
                     for (int rb = 0; rb < w.n_rb; ++rb) {
                         const uint32_t d = tmem + (uint32_t)(buf * TC_ACC_COLS + rb * TC_N);
                         for (int a = 0; a < w.n_atoms; ++a, ++it) {
                             const int st = it % TC_STAGES;
-                            mbar_wait(smem_u32(&s_full[st]), (it / TC_STAGES) & 1);
+                            mbar_wait_parked(smem_u32(&s_full[st]), (it / TC_STAGES) & 1);
                             tc_fence_after();
                             const uint32_t sa = ring + st * TC_STAGE_BYTES;
                             const uint64_t da = tc_smem_desc(sa);
@@ -323,7 +323,7 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
                 const int h = job.h, buf = jg & 1;
                 const float *w_col = stage_taps_window<GB_RC>(tap_col + (size_t)ji * P.tap_slot, job.col_im, h);
                 const int nblk_col = (2 * h + GB_RC + GB_RC - 1) / GB_RC;
-                mbar_wait(smem_u32(&s_tfull[buf]), (jg >> 1) & 1);
+                mbar_wait_parked(smem_u32(&s_tfull[buf]), (jg >> 1) & 1);
                 tc_fence_after();
                 TC_TR_ADD(1);
                 if (warp < TC_XFER_WARPS) {

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
         }
         __syncthreads();
         const int lo = s_lo, hi = s_hi;
-        for (int e = threadIdx.x; e < ne; e += GB_THREADS) rowtab[e] = (rowtab[e] - lo) * GB_TWP;
+        for (int e = threadIdx.x; e < ne; e += GB_THREADS) rowtab[e] = (rowtab[e] - lo) * (GB_TWP * 8);   // byte offsets into T
 
         // ---- row pass: image rows [lo, hi) -> T (complex) in shared memory ----
         const int cw = GB_TW + 2 * h + GB_RR;            // staged columns per row

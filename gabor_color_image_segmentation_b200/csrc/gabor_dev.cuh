@@ -2,6 +2,7 @@
 // gabor_tc.cu: row pass on the tcgen05 tensor cores, column pass on the FP32 pipe).
 // Reference: none (segmenter slot, BSD_metrics/script.py:30; spec in DESIGN.md section 3).
 #pragma once
+#include "async.cuh"
 #include "gabor.cuh"
 
 namespace gcis {
@@ -58,6 +59,14 @@ __device__ __forceinline__ void fma2_vs(u64 &acc, u64 a, float s)
 __device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi)
 {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+// 64-bit shared load at a 32-bit shared-window address (one IADD per address instead of generic pointer arithmetic)
+__device__ __forceinline__ u64 lds64(uint32_t addr)
+{
+    u64 v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
 }
 
 // Register-blocked sliding window shared by both passes:
@@ -121,8 +130,9 @@ __device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u6
             const float4 v = *reinterpret_cast<const float4 *>(xvec + m * 4);
             xr[0] = v.x; xr[1 % R] = v.y; xr[2 % R] = v.z; xr[3 % R] = v.w;
         } else {
+            xload(m, IntC<NIN>{}, xp);   // the block's first NIN inputs
 #pragma unroll
-            for (int uu = 0; uu < NIN; ++uu) xload(m * R + uu, xr[uu], xi[uu], xp[uu]);
+            for (int uu = 0; uu < NIN; ++uu) unpack2(xp[uu], xr[uu], xi[uu]);
         }
 #pragma unroll
         for (int uu = 0; uu < NIN; ++uu) {
@@ -376,7 +386,7 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
     const int nfull = th / GB_RC, tail = th - nfull * GB_RC;
     const bool thin_tail = h >= 0 && tail > 0 && tail <= GB_TAIL_MAX && nfull >= nwarps && P.W - x0 > GB_THIN_COLS;
     const int nrb = thin_tail ? nfull : (th + GB_RC - 1) / GB_RC;
-    const u64 *Tl = reinterpret_cast<const u64 *>(T) + lane;
+    const uint32_t tl = smem_u32(T) + 8u * lane;   // this lane's column of T in the shared window; the row table holds BYTE offsets
     // triangular first/last block of the sweep when the taps span at least one block (always for the BSDS bank)
     const int tri_d = (GB_TRI && h >= 0 && 2 * h >= GB_RC && nblk == (2 * h + 2 * GB_RC - 1) / GB_RC) ? (nblk - 1) * GB_RC - 2 * h : -1;
     int m1[2] = {0, 0};                      // exact integer moments of what this thread writes (normalisation)
@@ -447,7 +457,7 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
     // same bits.  r and col may differ from lane to lane.
     auto one_output = [&](int r, int col) {
         const int *rt = rowtab + r;
-        const u64 *Tc = reinterpret_cast<const u64 *>(T) + col;
+        const uint32_t tc = smem_u32(T) + 8u * col;
         u64 Pa = 0ull, Qa = 0ull;
         float Sa = 0.f;
         if constexpr (CT) {
@@ -455,7 +465,7 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
 #pragma unroll 4
             for (int u = 0; u <= 2 * h; ++u) {
                 float xr, xi;
-                unpack2(Tc[rt[u]], xr, xi);
+                unpack2(lds64(tc + (uint32_t)rt[u]), xr, xi);
                 const u64 w = tp[2 * h - u];
                 fma2_vs(Pa, w, xr);
                 if constexpr (CX) fma2_vs(Qa, w, xi);
@@ -464,7 +474,7 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
             const float *tp = w0 - (2 * h - GB_RC + 1);                                      // real tap 0
 #pragma unroll 4
             for (int u = 0; u <= 2 * h; ++u) {
-                const u64 xp = Tc[rt[u]];
+                const u64 xp = lds64(tc + (uint32_t)rt[u]);
                 const float w = tp[2 * h - u];
                 if constexpr (CX) {
                     fma2_vs(Pa, xp, w);
@@ -493,9 +503,16 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
         for (int i = 0; i < GB_RC; ++i) { Pv[i] = 0ull; Qv[i] = 0ull; Sv[i] = 0.f; }
         const int *rt = rowtab + rb * GB_RC;
         sweep<GB_RC, CT, CX>(
-            [&](int u, float &xr, float &xi, u64 &xp) {
-                xp = Tl[rt[u]];
-                unpack2(xp, xr, xi);
+            [&](int m, auto nin_c, u64 (&xp)[GB_RC]) {
+                // the block's eight row-table entries (byte offsets into T) as two 128-bit loads, then one add per row
+                constexpr int NIN = decltype(nin_c)::value;
+                const int4 *rp = reinterpret_cast<const int4 *>(rt + m * GB_RC);
+                const int4 a = rp[0];
+                int4 b = a;
+                if constexpr (NIN > 4) b = rp[1];
+                const int off[GB_RC] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int uu = 0; uu < NIN; ++uu) xp[uu] = lds64(tl + (uint32_t)off[uu]);
             },
             w0, nblk, Pv, Qv, Sv, nullptr, tri_d);
         emit_block(rb * GB_RC, Pv, Qv, Sv);

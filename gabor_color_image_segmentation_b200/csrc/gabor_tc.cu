@@ -300,22 +300,18 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
     } else if (warp < TC_COLW) {
         // =============================== column-pass warps ===============================
         const int D = P.C * P.S * P.O;
-        int jg = 0, cur_s = -1, cur_y0 = -1;
+        int jg = 0, cur_s = -1, cur_y0 = -1, cur_h = -1;
         TC_TR_ADD(0);
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const TcItem w = tc_decode(Q, item);
             const GaborScale &sc = P.scales[w.s];
             float *featb = P.feat + (size_t)w.b * D * P.feat_plane_stride;
-            if (w.s != cur_s || w.y0 != cur_y0) {
+            if (w.s != cur_s) {
                 // (the trailing barrier of the previous job guarantees nobody still reads the tables)
-                // row table relative to T for the scale's widest job (a job with half-width h starts hmax - h entries in)
-                const int ne = (w.th + GB_RC - 1) / GB_RC * GB_RC + 2 * w.hmax + 2 * GB_RC;
-                for (int e = threadIdx.x; e < ne; e += TC_COLT)
-                    rowtab[e] = (reflect_index(w.y0 - w.hmax + min(e, w.th + 2 * w.hmax - 1), P.H) - w.lo) * GB_TWP;
-                if (w.s != cur_s)   // column taps of every job of the scale
-                    for (int ji = 0; ji < w.n_jobs; ++ji)
-                        stage_taps<GB_RC>(tap_col + (size_t)ji * P.tap_slot, P.taps, sc.jobs[ji].col_re, sc.jobs[ji].col_im, sc.jobs[ji].h, TC_COLT);
-                cur_s = w.s; cur_y0 = w.y0;
+                // column taps of every job of the scale
+                for (int ji = 0; ji < w.n_jobs; ++ji)
+                    stage_taps<GB_RC>(tap_col + (size_t)ji * P.tap_slot, P.taps, sc.jobs[ji].col_re, sc.jobs[ji].col_im, sc.jobs[ji].h, TC_COLT);
+                cur_s = w.s; cur_h = -1;
             }
             TC_TR_ADD(4);
             for (int ji = 0; ji < w.n_jobs; ++ji, ++jg) {
@@ -323,6 +319,14 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
                 const int h = job.h, buf = jg & 1;
                 const float *w_col = stage_taps_window<GB_RC>(tap_col + (size_t)ji * P.tap_slot, job.col_im, h);
                 const int nblk_col = (2 * h + GB_RC + GB_RC - 1) / GB_RC;
+                if (h != cur_h || w.y0 != cur_y0) {
+                    // row table of the job: BYTE offset into T of every input row of the column pass (reflect-folded); entry 0
+                    // is row y0 - h, so a block's eight entries are two aligned 128-bit loads (col_pass)
+                    const int ne = (w.th + GB_RC - 1) / GB_RC * GB_RC + 2 * h + 2 * GB_RC;
+                    for (int e = threadIdx.x; e < ne; e += TC_COLT)
+                        rowtab[e] = (reflect_index(w.y0 - h + min(e, w.th + 2 * h - 1), P.H) - w.lo) * (GB_TWP * 8);
+                    cur_h = h; cur_y0 = w.y0;
+                }
                 mbar_wait_parked(smem_u32(&s_tfull[buf]), (jg >> 1) & 1);
                 tc_fence_after();
                 TC_TR_ADD(1);
@@ -351,7 +355,7 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
                 const int d0 = (w.c * P.S + w.s) * P.O;
                 float *f0 = featb + (size_t)(d0 + job.out0) * P.feat_plane_stride;
                 float *f1 = job.out1 >= 0 ? featb + (size_t)(d0 + job.out1) * P.feat_plane_stride : nullptr;
-                const int *rt = rowtab + (w.hmax - h);
+                const int *rt = rowtab;
                 const bool cx = job.row_im >= 0, ct = job.col_im >= 0;
                 long long *st0 = STATS ? P.stats + ((size_t)w.b * D + d0 + job.out0) * GB_STAT_SLOTS : nullptr;
                 long long *st1 = STATS && job.out1 >= 0 ? P.stats + ((size_t)w.b * D + d0 + job.out1) * GB_STAT_SLOTS : nullptr;

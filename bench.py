@@ -56,6 +56,11 @@ class ClockSampler(threading.Thread):
         self.gpu, self.samples, self.stop_flag = gpu_index, [], threading.Event()
         self.ready = threading.Event()   # set once the first sample exists: start_and_wait() returns only then
 
+    def mark(self):
+        """Start of the timed region: drop the idle samples (the last one stays as a fallback for a very short region)."""
+        self.idle_last = self.samples[-1] if self.samples else None
+        self.samples = []
+
     def start_and_wait(self, timeout=5.0):
         """NVML initialisation can take longer than a short timed region: wait for the first sample before timing."""
         self.start()
@@ -116,6 +121,8 @@ class ClockSampler(threading.Thread):
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
+        if not self.samples and getattr(self, "idle_last", None):
+            self.samples = [self.idle_last]
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         sm = sorted(float(s[0]) for s in self.samples)
@@ -238,7 +245,7 @@ def run_gpu(args):
     # ---- value: device-resident inputs, CUDA events, max over ranks ----
     sampler = ClockSampler(local).start_and_wait()
     barrier()
-    sampler.samples.clear()   # keep only the samples taken under load
+    sampler.mark()            # keep only the samples taken under load
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -479,7 +486,7 @@ def run_gpu_strong(args):
     plan.pipeline_host(*h_chunks[0], len(chunks[0]))
     sampler = ClockSampler(local).start_and_wait()
     barrier()
-    sampler.samples.clear()   # keep only the samples taken under load
+    sampler.mark()            # keep only the samples taken under load
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -591,7 +598,7 @@ def run_config(args):
         plan.pipeline_device(d_img, d_gt, d_idx); plan.fetch()
     sampler = ClockSampler(0).start_and_wait()
     torch.cuda.synchronize()
-    sampler.samples.clear()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):

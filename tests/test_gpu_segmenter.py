@@ -27,7 +27,11 @@ def _torch():
     ((24, 33), (3, 4), "rgb"),          # kernel half-width (27) exceeds the image: multiple reflections
     ((70, 45), (2, 6), "opponent"),
     ((37, 64), (2, 5), "lab"),          # odd orientation count: unpaired orientations
-    ((130, 97), (4, 6), "rgb"),
+    ((130, 97), (4, 6), "rgb"),         # last strip 1 column wide (lanes-on-rows path), 2 leftover rows (thin tail)
+    ((41, 34), (2, 4), "rgb"),          # last strip 2 columns, 1 leftover row on a tile shorter than the warp count
+    ((106, 36), (3, 2), "rgb"),         # last strip 4 columns (widest thin strip), 2 leftover rows
+    ((99, 37), (2, 3), "rgb"),          # last strip 5 columns: regular sweep; 3 leftover rows: masked block
+    ((9, 68), (1, 6), "rgb"),           # one full block + 1 row; taps (15) span two blocks: triangular first/last only
 ])
 def test_gabor_features_small(shape, bank_args, space):
     torch = _torch()

@@ -51,7 +51,7 @@ constexpr int TC_COLW = TC_COLW_N;             // column-pass warps: 3 per SM su
 constexpr int TC_COLT = TC_COLW * 32;
 constexpr int TC_TMA_WARP = TC_COLW, TC_MMA_WARP = TC_COLW + 1;
 constexpr int TC_THREADS = TC_COLT + 64;
-constexpr int TC_STAGES = 3;
+constexpr int TC_STAGES = 3;                   // deepest TMA ring; a plan whose T needs the room runs with 2 (TcParams::stages)
 constexpr int TC_MROWS = 128;                  // rows per MMA (M)
 constexpr int TC_N = 2 * GB_TW;                // 64: (column, re|im)
 constexpr int TC_KATOM = 64;                   // bf16 elements per 128-byte swizzle atom row
@@ -59,10 +59,11 @@ constexpr int TC_A_BYTES = TC_MROWS * 128;     // 16 KB
 constexpr int TC_B_BYTES = TC_N * 128;         // 8 KB per split term
 constexpr int TC_SPLIT = 3;
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_SPLIT * TC_B_BYTES;   // 40 KB
-constexpr int TC_MAX_RB = 3;                   // row blocks per accumulator: T holds up to 384 rows
-constexpr int TC_ACC_COLS = TC_MAX_RB * TC_N;  // 192 TMEM columns per accumulator
-constexpr int TC_TMEM_COLS = 512;              // allocation (power of two >= 2 * 192)
-constexpr int TC_XFER_WARPS = 4 * TC_MAX_RB;   // warps that move TMEM -> shared memory (one per lane quadrant x row block)
+constexpr int TC_MAX_RB = 4;                   // row blocks per accumulator: T holds up to 512 rows (a 481-row portrait image in one tile)
+constexpr int TC_ACC_COLS = TC_MAX_RB * TC_N;  // 256 TMEM columns per accumulator
+constexpr int TC_TMEM_COLS = 512;              // allocation: two accumulators
+constexpr int TC_XFER_RB = TC_COLW / 4;        // row blocks moved TMEM -> shared memory at a time (one warp per lane quadrant and block)
+static_assert(TC_COLW % 4 == 0 && TC_COLW >= 4, "a column warp reads the TMEM lane quadrant warp % 4");
 
 struct TcParams {
     GaborParams g;                // shapes, feature tensor, FP32 tap table (column taps), scales
@@ -73,6 +74,7 @@ struct TcParams {
     int hmax[GB_MAX_SCALES], n_jobs[GB_MAX_SCALES];   // copies of the scale table for the single-thread roles
     int max_jobs;                 // jobs of the scale with the most jobs (column-tap slots in shared memory)
     int plane_rows;               // rows of the bf16 plane tensor = B * C * H
+    int stages;                   // depth of the TMA ring (2 or 3)
 };
 
 // instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = 64 (cute::UMMA::InstrDescriptor bit layout)
@@ -220,7 +222,8 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
     const uint32_t raw = smem_u32(tc_smem_raw);
     const uint32_t ring = (raw + 1023u) & ~1023u;
     unsigned char *base = tc_smem_raw + (ring - raw);
-    float2 *T = reinterpret_cast<float2 *>(base + TC_STAGES * TC_STAGE_BYTES);       // [nsrc_cap][GB_TWP]
+    const int n_st = Q.stages;
+    float2 *T = reinterpret_cast<float2 *>(base + n_st * TC_STAGE_BYTES);            // [nsrc_cap][GB_TWP]
     float *tap_col = reinterpret_cast<float *>(T + (((size_t)P.nsrc_cap * GB_TWP + 1) & ~(size_t)1));   // 16-byte aligned: 128-bit tap loads
     int *rowtab = reinterpret_cast<int *>(tap_col + (size_t)Q.max_jobs * P.tap_slot);
 
@@ -228,7 +231,7 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
     // ---- one-time set-up ----
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_STAGES; ++i) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_empty[i]), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_tfull[i]), 1); mbar_init(smem_u32(&s_tempty[i]), TC_XFER_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_tfull[i]), 1); mbar_init(smem_u32(&s_tempty[i]), TC_COLW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC_MMA_WARP) {   // tensor memory: the whole warp allocates, the address lands in shared memory
@@ -251,8 +254,8 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
                 for (int ji = 0; ji < w.n_jobs; ++ji)
                     for (int rb = 0; rb < w.n_rb; ++rb)
                         for (int a = 0; a < w.n_atoms; ++a, ++it) {
-                            const int st = it % TC_STAGES;
-                            mbar_wait_parked(smem_u32(&s_empty[st]), ((it / TC_STAGES) & 1) ^ 1);
+                            const int st = it % n_st;
+                            mbar_wait_parked(smem_u32(&s_empty[st]), ((it / n_st) & 1) ^ 1);
                             const uint32_t fb = smem_u32(&s_full[st]);
                             const uint32_t dst = ring + st * TC_STAGE_BYTES;
                             mbar_expect_tx(fb, TC_STAGE_BYTES);
@@ -277,8 +280,8 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
                     for (int rb = 0; rb < w.n_rb; ++rb) {
                         const uint32_t d = tmem + (uint32_t)(buf * TC_ACC_COLS + rb * TC_N);
                         for (int a = 0; a < w.n_atoms; ++a, ++it) {
-                            const int st = it % TC_STAGES;
-                            mbar_wait_parked(smem_u32(&s_full[st]), (it / TC_STAGES) & 1);
+                            const int st = it % n_st;
+                            mbar_wait_parked(smem_u32(&s_full[st]), (it / n_st) & 1);
                             tc_fence_after();
                             const uint32_t sa = ring + st * TC_STAGE_BYTES;
                             const uint64_t da = tc_smem_desc(sa);
@@ -330,9 +333,9 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
                 mbar_wait_parked(smem_u32(&s_tfull[buf]), (jg >> 1) & 1);
                 tc_fence_after();
                 TC_TR_ADD(1);
-                if (warp < TC_XFER_WARPS) {
-                    const int rb = warp >> 2, q = warp & 3;
-                    if (rb < w.n_rb) {
+                {   // every column warp moves its lane quadrant of the row blocks warp / 4, warp / 4 + TC_XFER_RB, ...
+                    const int q = warp & 3;
+                    for (int rb = warp >> 2; rb < w.n_rb; rb += TC_XFER_RB) {
                         const int r = rb * TC_MROWS + q * 32 + lane;                 // T row of this thread
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
@@ -432,11 +435,11 @@ struct GaborTcPlan {
     CUtensorMap map_table;
 };
 
-size_t gabor_tc_smem_bytes(int nsrc, int hmax, int th_max, int max_jobs)
+size_t gabor_tc_smem_bytes(int nsrc, int hmax, int th_max, int max_jobs, int stages)
 {
     const int tap_slot = round_up(2 * (2 * hmax + 1 + 2 * GB_TAP_PAD + 2) + 8, 4);
     const int rowtab = round_up((th_max + GB_RC - 1) / GB_RC * GB_RC + 2 * hmax + 2 * GB_RC, 4);
-    return 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + sizeof(float2) * (((size_t)nsrc * GB_TWP + 1) & ~(size_t)1) + sizeof(float) * (size_t)tap_slot * max_jobs +
+    return 1024 + (size_t)stages * TC_STAGE_BYTES + sizeof(float2) * (((size_t)nsrc * GB_TWP + 1) & ~(size_t)1) + sizeof(float) * (size_t)tap_slot * max_jobs +
            sizeof(int) * (size_t)rowtab;
 }
 
@@ -468,31 +471,49 @@ GaborTcPlan *gabor_tc_plan_new(const GaborBankHost &bank, int H, int W, int C, i
         tp->q.n_jobs[s] = bank.scales[s].n_jobs;
     }
     tp->q.max_jobs = max_jobs;
-    int nsrc_cap;
-    if (H <= cap && gabor_tc_smem_bytes(H, hmax, H, max_jobs) <= budget) {
-        nsrc_cap = H;
-        for (int s = 0; s < bank.S; ++s) { p.TH[s] = H; p.n_vt[s] = 1; }
-    } else {
-        nsrc_cap = 0;
-        for (int rows = 2 * hmax + GB_RC; rows <= cap && gabor_tc_smem_bytes(rows, hmax, rows, max_jobs) <= budget; rows += GB_RC) nsrc_cap = rows;
-        if (nsrc_cap == 0) { delete tp; return nullptr; }
+    // Tile heights for a ring of `stages` stages: the whole image height if T fits beside the ring, else vertical tiles
+    // (each pays the 2 hmax halo rows of the row pass again).  Returns the number of tiles of the widest scale, 0 = no fit.
+    struct Layout { int nsrc_cap = 0, TH[GB_MAX_SCALES] = {0}, n_vt[GB_MAX_SCALES] = {0}, tiles = 0; };
+    auto layout = [&](int stages) {
+        Layout L;
+        if (H <= cap && gabor_tc_smem_bytes(H, hmax, H, max_jobs, stages) <= budget) {
+            L.nsrc_cap = H;
+            for (int s = 0; s < bank.S; ++s) { L.TH[s] = H; L.n_vt[s] = 1; }
+            L.tiles = 1;
+            return L;
+        }
+        for (int rows = 2 * hmax + GB_RC; rows <= cap && gabor_tc_smem_bytes(rows, hmax, rows, max_jobs, stages) <= budget; rows += GB_RC) L.nsrc_cap = rows;
+        if (L.nsrc_cap == 0) return L;
         for (int s = 0; s < bank.S; ++s) {
             const int hs = bank.scales[s].hmax;
-            int th = (nsrc_cap - 2 * hs) / GB_RC * GB_RC;
-            if (th < GB_RC) { delete tp; return nullptr; }
+            int th = (L.nsrc_cap - 2 * hs) / GB_RC * GB_RC;
+            if (th < GB_RC) { L.tiles = 0; return L; }
             if (th > H) th = H;
-            p.n_vt[s] = ceil_div(H, th);
-            p.TH[s] = round_up(ceil_div(H, p.n_vt[s]), GB_RC);
-            if (p.TH[s] > th) p.TH[s] = th;
-            p.n_vt[s] = ceil_div(H, p.TH[s]);
+            L.n_vt[s] = ceil_div(H, th);
+            L.TH[s] = round_up(ceil_div(H, L.n_vt[s]), GB_RC);
+            if (L.TH[s] > th) L.TH[s] = th;
+            L.n_vt[s] = ceil_div(H, L.TH[s]);
+            L.tiles = std::max(L.tiles, L.n_vt[s]);
         }
+        return L;
+    };
+    // three stages unless two stages leave room for a taller T that saves vertical tiles (a 481-row portrait image:
+    // one tile of 60 row blocks, five per column warp, instead of two tiles with their halo)
+    Layout L = layout(TC_STAGES);
+    tp->q.stages = TC_STAGES;
+    if (L.tiles != 1) {
+        const Layout L2 = layout(2);
+        if (L2.tiles > 0 && (L.tiles == 0 || L2.tiles < L.tiles)) { L = L2; tp->q.stages = 2; }
     }
+    if (L.tiles == 0) { delete tp; return nullptr; }
+    const int nsrc_cap = L.nsrc_cap;
+    for (int s = 0; s < bank.S; ++s) { p.TH[s] = L.TH[s]; p.n_vt[s] = L.n_vt[s]; }
     int th_max = 0;
     for (int s = 0; s < bank.S; ++s) th_max = std::max(th_max, p.TH[s]);
     p.nsrc_cap = nsrc_cap;
     p.tap_slot = round_up(2 * (2 * hmax + 1 + 2 * GB_TAP_PAD + 2) + 8, 4);
     p.rowtab_cap = round_up((th_max + GB_RC - 1) / GB_RC * GB_RC + 2 * hmax + 2 * GB_RC, 4);
-    tp->smem = gabor_tc_smem_bytes(nsrc_cap, hmax, th_max, max_jobs);
+    tp->smem = gabor_tc_smem_bytes(nsrc_cap, hmax, th_max, max_jobs, tp->q.stages);
     std::vector<int> order(bank.S);
     for (int s = 0; s < bank.S; ++s) order[s] = s;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bank.scales[a].hmax > bank.scales[b].hmax; });

@@ -558,6 +558,7 @@ CONFIGS = {
     "dense_lab": (321, 481, 8, 32, "lab", True, "configs[2]: dense bank 8 scales x 12 orientations on Lab channels (D = 288)"),
     "normalised": (321, 481, 8, 200, "rgb", False, "configs[1] with per-feature normalisation (DESIGN.md 3.6)"),
     "smoothed": (321, 481, 8, 100, "rgb", False, "configs[1] with feature smoothing 0.5 sigma_s and normalisation"),
+    "portrait": (481, 321, 8, 200, "rgb", False, "configs[1] on portrait images (481 rows x 321 columns, as a third of BSDS500)"),
 }
 
 
@@ -569,7 +570,7 @@ def run_config(args):
     from gabor_color_image_segmentation_b200.pipeline import init_indices_for
     from gabor_color_image_segmentation_b200.synth import synth_image, synth_ground_truths
     Hc, Wc, k, B, space, dense, what = CONFIGS[args.config]
-    B = args.images if args.images != 200 or args.config in ("normalised",) else B
+    B = args.images if args.images != 200 or args.config in ("normalised", "portrait") else B
     os.environ["GCIS_LANES"] = "1"
     torch.cuda.set_device(0)
     small = max(1, max(Hc, Wc) // 1024)                      # large images: upscaled synthetic content + noise

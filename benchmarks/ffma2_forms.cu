@@ -2,6 +2,7 @@
 // register pattern of the filter bank's column pass: 16 accumulator pairs, 8 tap pairs, 8 inputs per block.
 //   form 0: acc += W * {x, x}   ptxas folds the duplicated scalar into the FFMA2 ".F32" broadcast operand
 //   form 1: acc += W * X        X a genuine register pair
+//   form 2: acc += X * {w, w}   the repeated operand is the pair, the varying one a scalar (k-means score loop candidate)
 // Prints one JSON line with TFLOP/s per form (2 FLOP per lane-FMA, 2 lanes per FFMA2).
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -29,7 +30,13 @@ __global__ void __launch_bounds__(256) k(float *out, const float *in, int iters)
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const u64 ww = w[(i - u + 8) & 15];
-                if (FORM == 0) {
+                if (FORM == 2) {   // acc += X * {w, w}: the PAIR operand is the one that repeats (x[u] for 16 FMAs), the scalar varies
+                    u64 b;
+                    float wl, wh;
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(wl), "=f"(wh) : "l"(ww));
+                    asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(wl));
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[i]) : "l"(xp[u]), "l"(b));
+                } else if (FORM == 0) {
                     u64 b;
                     asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(x[u]));
                     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[i]) : "l"(ww), "l"(b));
@@ -79,7 +86,7 @@ int main()
     float h[128];
     for (int i = 0; i < 128; ++i) h[i] = 1e-3f * (i % 7) - 2e-3f;
     cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
-    const double t0 = run<0>(out, in, blocks, iters), t1 = run<1>(out, in, blocks, iters);
-    printf("{\"ffma2_scalar_operand_tflops\": %.2f, \"ffma2_pair_operand_tflops\": %.2f}\n", t0, t1);
+    const double t0 = run<0>(out, in, blocks, iters), t1 = run<1>(out, in, blocks, iters), t2 = run<2>(out, in, blocks, iters);
+    printf("{\"ffma2_scalar_operand_tflops\": %.2f, \"ffma2_pair_operand_tflops\": %.2f, \"ffma2_repeated_pair_varying_scalar_tflops\": %.2f}\n", t0, t1, t2);
     return cudaGetLastError() != cudaSuccess;
 }

@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gabor_bank_kernel(const __grid_
         const bool cx = job.row_im >= 0, ct = job.col_im >= 0;
         long long *st0 = STATS ? P.stats + ((size_t)b * D + d0 + job.out0) * GB_STAT_SLOTS : nullptr;
         long long *st1 = STATS && job.out1 >= 0 ? P.stats + ((size_t)b * D + d0 + job.out1) * GB_STAT_SLOTS : nullptr;
-        col_pass_dispatch<STATS>(cx, ct, P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1, GB_WARPS, st0, st1, h);
+        col_pass_dispatch<STATS>(cx, ct, P, T, rowtab, w_col, nblk_col, y0, th, x0, f0, f1, GB_WARPS, st0, st1, h, SmemTaps{w_col});
         GB_TR_ADD(3);
     }
 #ifdef GB_TRACE

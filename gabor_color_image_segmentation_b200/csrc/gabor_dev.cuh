@@ -93,16 +93,17 @@ constexpr int GB_SWEEP_UNR = GB_SWEEP_UNROLL;   // pairs of blocks per unrolled 
 // 16 % fewer FMAs for the 15/29/55/109-tap bank, same sums (x * 0 added to an accumulator leaves its value).
 template <int N> struct IntC { static constexpr int value = N; };
 
-template <int R, bool CT, bool CX, class XLoad>
-__device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u64 (&P)[R], u64 (&Q)[R], float (&S)[R],
-                                      const float *xvec = nullptr, int d = -1)
-{
-    // The window of block m is taps [base - m R, base - m R + 2R): its upper half is the lower half of
-    // block m - 1, so each block loads only its R new taps (the tap loads are warp-uniform shared loads
-    // and the load pipe, not the FMA pipe, bounds the row pass) and two register halves swap roles.
-    u64 ca[CT ? R : 1], cb[CT ? R : 1];
-    float ra[CT ? 1 : R], rb[CT ? 1 : R];
-    auto load_half = [&](int m, u64 (&c)[CT ? R : 1], float (&r)[CT ? 1 : R]) {
+// Tap source of sweep(): half(m, c, r) delivers the R new taps of block m (complex pairs in c, real taps in r).
+// SmemTaps reads the window stage_taps() laid out in shared memory (warp-uniform 128-bit loads into ordinary registers);
+// a kernel may pass a source of its own (gabor_tc.cu: the kernel's parameter space, so the taps live in UNIFORM registers
+// and the packed FMA reads only its accumulator pair and one scalar from the register file).
+struct SmemTaps {
+    static constexpr bool DIRECT = false;   // the taps are held in registers half a window at a time (half())
+    const float *w0;   // window of block 0; the window moves down by R taps per block
+    template <int R> __device__ __forceinline__ u64 tap(int, int) const { return 0ull; }
+    template <int R, bool CT>
+    __device__ __forceinline__ void half(int m, u64 (&c)[CT ? R : 1], float (&r)[CT ? 1 : R]) const
+    {
         if constexpr (CT) {
             const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(w0 - (ptrdiff_t)m * 2 * R);
 #pragma unroll
@@ -118,6 +119,20 @@ __device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u6
                 r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
             }
         }
+    }
+};
+
+template <int R, bool CT, bool CX, class XLoad, class Taps>
+__device__ __forceinline__ void sweep(XLoad xload, const Taps &taps, int nblk, u64 (&P)[R], u64 (&Q)[R], float (&S)[R],
+                                      const float *xvec = nullptr, int d = -1)
+{
+    // The window of block m is taps [base - m R, base - m R + 2R): its upper half is the lower half of
+    // block m - 1, so each block loads only its R new taps (the tap loads are warp-uniform shared loads
+    // and the load pipe, not the FMA pipe, bounds the row pass) and two register halves swap roles.
+    u64 ca[CT ? R : 1], cb[CT ? R : 1];
+    float ra[CT ? 1 : R], rb[CT ? 1 : R];
+    auto load_half = [&](int m, u64 (&c)[CT ? R : 1], float (&r)[CT ? 1 : R]) {
+        if constexpr (!Taps::DIRECT) taps.template half<R, CT>(m, c, r);
     };
     // MODE 0: all R x R products; 1: first block (outputs i <= u); 2: last block (outputs i >= u + DD)
     auto block = [&](auto mode_c, auto dd_c, int m, const u64 (&clo)[CT ? R : 1], const u64 (&chi)[CT ? R : 1],
@@ -134,21 +149,46 @@ __device__ __forceinline__ void sweep(XLoad xload, const float *w0, int nblk, u6
 #pragma unroll
             for (int uu = 0; uu < NIN; ++uu) unpack2(xp[uu], xr[uu], xi[uu]);
         }
+        if constexpr (Taps::DIRECT && CT) {
+            // A DIRECT source hands out tap t of the block's window where it is used (tap(m, t)); the products are issued
+            // tap by tap, t descending: one or two taps are live at a time (they fit the uniform registers), and every
+            // output still adds its products in the order uu = 0, 1, ... of the loop below: the same bits.
 #pragma unroll
-        for (int uu = 0; uu < NIN; ++uu) {
+            for (int t = 2 * R - 2; t >= 0; --t) {
+                bool any = false;
 #pragma unroll
-            for (int i = 0; i < R; ++i) {
-                if (MODE == 1 && i > uu) continue;
-                if (MODE == 2 && i < uu + DD) continue;
-                const int t = i - uu + R - 1;
-                if constexpr (CT) {
-                    const u64 w = t < R ? clo[t % R] : chi[t % R];
+                for (int i = 0; i < R; ++i) {
+                    const int uu = i - t + R - 1;
+                    if (uu < 0 || uu >= NIN || (MODE == 1 && i > uu) || (MODE == 2 && i < uu + DD)) continue;
+                    any = true;
+                }
+                if (!any) continue;
+                const u64 w = taps.template tap<R>(m, t);
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const int uu = i - t + R - 1;
+                    if (uu < 0 || uu >= NIN || (MODE == 1 && i > uu) || (MODE == 2 && i < uu + DD)) continue;
                     fma2_vs(P[i], w, xr[uu]);
                     if constexpr (CX) fma2_vs(Q[i], w, xi[uu]);
-                } else {
-                    const float w = t < R ? rlo[t % R] : rhi[t % R];
-                    if constexpr (CX) fma2_vs(P[i], xp[uu], w);
-                    else S[i] = fmaf(w, xr[uu], S[i]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int uu = 0; uu < NIN; ++uu) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    if (MODE == 1 && i > uu) continue;
+                    if (MODE == 2 && i < uu + DD) continue;
+                    const int t = i - uu + R - 1;
+                    if constexpr (CT) {
+                        const u64 w = t < R ? clo[t % R] : chi[t % R];
+                        fma2_vs(P[i], w, xr[uu]);
+                        if constexpr (CX) fma2_vs(Q[i], w, xi[uu]);
+                    } else {
+                        const float w = t < R ? rlo[t % R] : rhi[t % R];
+                        if constexpr (CX) fma2_vs(P[i], xp[uu], w);
+                        else S[i] = fmaf(w, xr[uu], S[i]);
+                    }
                 }
             }
         }
@@ -372,12 +412,14 @@ constexpr int GB_TAIL_MAX = 2;   // leftover rows (th mod GB_RC) up to this many
 #endif
 constexpr int GB_THIN_COLS = 4;  // strips with at most this many image columns get the lanes-on-rows path
 
-template <bool CX, bool CT, bool STATS = false>
+template <bool CX, bool CT, bool STATS, class Taps>
 __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, const int *rowtab, const float *w0,
-                                         int nblk, int y0, int th, int x0, float *feat0, float *feat1, int nwarps = GB_WARPS,
-                                         long long *st0 = nullptr, long long *st1 = nullptr, int h = -1)
+                                         int nblk, int y0, int th, int x0, float *feat0, float *feat1, int nwarps,
+                                         long long *st0, long long *st1, int h, const Taps &taps)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // (the shuffle tells the compiler that the warp index is warp uniform: loop counters and addresses derived from it may
+    // then live in uniform registers)
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     // BSDS images are 321 or 481 rows = whole blocks of GB_RC rows + ONE row: as a masked block that row costs a full
     // block and unbalances the warps (41 blocks over 16 warps: one SM sub-partition gets 11, the others 10).  Up to
     // GB_TAIL_MAX leftover rows are instead computed one at a time (same taps in the same order: same bits) by the
@@ -514,7 +556,7 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
 #pragma unroll
                 for (int uu = 0; uu < NIN; ++uu) xp[uu] = lds64(tl + (uint32_t)off[uu]);
             },
-            w0, nblk, Pv, Qv, Sv, nullptr, tri_d);
+            taps, nblk, Pv, Qv, Sv, nullptr, tri_d);
         emit_block(rb * GB_RC, Pv, Qv, Sv);
     }
     if (thin_tail)
@@ -532,16 +574,17 @@ __device__ __forceinline__ void col_pass(const GaborParams &P, const float2 *T, 
 
 // run-time (CX, CT) -> compile-time instantiation; STATS (the moments of the normalisation) is a property of the whole
 // kernel, so that the kernel without it carries none of its registers
-template <bool STATS>
+// `ctaps`: the tap source of the sweeps with COMPLEX column taps (real taps always come from the staged window w0)
+template <bool STATS, class CTaps>
 __device__ __forceinline__ void col_pass_dispatch(bool cx, bool ct, const GaborParams &P, const float2 *T, const int *rowtab,
                                                   const float *w0, int nblk, int y0, int th, int x0, float *f0, float *f1,
-                                                  int nwarps, long long *st0, long long *st1, int h)
+                                                  int nwarps, long long *st0, long long *st1, int h, const CTaps &ctaps)
 {
-#define GB_COL(CXV, CTV) col_pass<CXV, CTV, STATS>(P, T, rowtab, w0, nblk, y0, th, x0, f0, f1, nwarps, st0, st1, h)
-    if (cx && ct) GB_COL(true, true);
-    else if (cx) GB_COL(true, false);
-    else if (ct) GB_COL(false, true);
-    else GB_COL(false, false);
+#define GB_COL(CXV, CTV, TAPS) col_pass<CXV, CTV, STATS>(P, T, rowtab, w0, nblk, y0, th, x0, f0, f1, nwarps, st0, st1, h, TAPS)
+    if (cx && ct) GB_COL(true, true, ctaps);
+    else if (cx) GB_COL(true, false, SmemTaps{w0});
+    else if (ct) GB_COL(false, true, ctaps);
+    else GB_COL(false, false, SmemTaps{w0});
 #undef GB_COL
 }
 

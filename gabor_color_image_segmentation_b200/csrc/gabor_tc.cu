@@ -31,6 +31,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "async.cuh"
@@ -43,11 +44,13 @@ using namespace gbdev;
 namespace {
 
 #ifndef TC_COLW_N
-#define TC_COLW_N 12
+#define TC_COLW_N 16
 #endif
-constexpr int TC_COLW = TC_COLW_N;             // column-pass warps: 3 per SM sub-partition; with the two issuing warps the CTA is 14
-                                               // warps, at most 4 per sub-partition = 128 registers per thread (18 warps: 96, and
-                                               // the triangular sweep of gabor_dev.cuh spills: 16 warps 94.7, 12 warps 71.6 us/image)
+constexpr int TC_COLW = TC_COLW_N;             // column-pass warps: 4 per SM sub-partition.  With the complex column taps in uniform
+                                               // registers (ConstTaps) the kernel needs 62 registers per thread, so the warp count
+                                               // is free: 12 / 16 / 20 / 24 / 28 warps -> 12.9 / 11.5 / 11.9 / 12.3 / 12.4 ms per 200
+                                               // images (with 12 warps the compiler keeps the taps in ordinary registers: 116).
+                                               // Before, with the taps in ordinary registers (128 per thread): 13.5 ms at 12 warps.
 constexpr int TC_COLT = TC_COLW * 32;
 constexpr int TC_TMA_WARP = TC_COLW, TC_MMA_WARP = TC_COLW + 1;
 constexpr int TC_THREADS = TC_COLT + 64;
@@ -65,6 +68,9 @@ constexpr int TC_TMEM_COLS = 512;              // allocation: two accumulators
 constexpr int TC_XFER_RB = TC_COLW / 4;        // row blocks moved TMEM -> shared memory at a time (one warp per lane quadrant and block)
 static_assert(TC_COLW % 4 == 0 && TC_COLW >= 4, "a column warp reads the TMEM lane quadrant warp % 4");
 
+constexpr int TC_CTAP_CAP = 6144;              // complex column taps the constant table holds (48 KB; the 4 x 6 bank needs 1440)
+constexpr int TC_CTAP_JOBS = 8;                // jobs per scale the constant table covers
+
 struct TcParams {
     GaborParams g;                // shapes, feature tensor, FP32 tap table (column taps), scales
     int ksteps[GB_MAX_SCALES];    // K steps of 16 per scale: ceil((32 + 2 hmax_s + kshift_s) / 16)
@@ -75,7 +81,22 @@ struct TcParams {
     int max_jobs;                 // jobs of the scale with the most jobs (column-tap slots in shared memory)
     int plane_rows;               // rows of the bf16 plane tensor = B * C * H
     int stages;                   // depth of the TMA ring (2 or 3)
+    // Complex column taps live in CONSTANT memory (c_ctaps below), in the layout stage_taps() gives them in shared memory
+    // (slot of scale s, job ji at complex index ctap_base[s] + ji * ctap_slot[s]; tap j of a job at 1 + GB_TAP_PAD + j).
+    int ctap_base[GB_MAX_SCALES], ctap_slot[GB_MAX_SCALES];
+    int ctap_w0[GB_MAX_SCALES * TC_CTAP_JOBS];   // complex index of the block-0 window of (scale, job); -1: real column taps
+    // half-width and kind of every job once more, here, so that the column warps derive their loop bounds and tap
+    // indices from parameters, block indices and loop counters only: the compiler then keeps them in uniform registers
+    int job_h[GB_MAX_SCALES * TC_CTAP_JOBS], job_kind[GB_MAX_SCALES * TC_CTAP_JOBS];   // kind: bit 0 complex row taps, bit 1 complex column taps
 };
+
+// The complex column taps of the bank the kernel runs (uploaded by gabor_tc_launch when the bank changes).  The sweeps read
+// them with uniform constant loads (LDCU.64) into UNIFORM registers and FFMA2 takes the pair as a uniform operand: per
+// packed FMA the register file delivers one accumulator pair and one scalar instead of two pairs (a stream of FFMA2 with
+// two register-pair operands sustains 0.75 of the FP32 peak, benchmarks/ffma2_forms.cu), the taps cost no shared-memory
+// loads and no ordinary registers (128 -> 62 registers per thread).  (From the kernel's parameter space instead the
+// compiler kept the taps in ordinary registers.)
+__constant__ float2 c_ctaps[TC_CTAP_CAP];
 
 // instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = 64 (cute::UMMA::InstrDescriptor bit layout)
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_MROWS >> 4) << 24);
@@ -203,6 +224,22 @@ __device__ __forceinline__ TcItem tc_decode(const TcParams &Q, int item)
     return it;
 }
 
+// Tap source of the column sweeps (gabor_dev.cuh: sweep()): the complex taps of one job from the constant table.
+struct ConstTaps {
+    int w0c;   // complex index of the block-0 window (warp uniform: derived from the work item and the job counter only)
+    static constexpr bool DIRECT = true;   // a tap is loaded where it is used: one or two taps are live at a time
+    template <int R, bool CT>
+    __device__ __forceinline__ void half(int, u64 (&)[CT ? R : 1], float (&)[CT ? 1 : R]) const {}
+    template <int R>
+    __device__ __forceinline__ u64 tap(int m, int t) const   // tap t (0 .. 2R - 2) of the window of block m
+    {
+        const float2 v = c_ctaps[w0c - m * R + t];
+        u64 w;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(w) : "f"(v.x), "f"(v.y));
+        return w;
+    }
+};
+
 // Persistent kernel: one CTA per SM walks the work items i = blockIdx.x, blockIdx.x + gridDim.x, ...; the
 // orientation jobs of consecutive items form one stream through the TMA ring and the two TMEM accumulators,
 // so the tensor cores already work on the next item while the column warps finish the current one.
@@ -215,7 +252,7 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
     __shared__ __align__(8) unsigned long long s_full[TC_STAGES], s_empty[TC_STAGES], s_tfull[2], s_tempty[2];
     __shared__ uint32_t s_tmem;
     const GaborParams &P = Q.g;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // (warp uniform for the compiler)
     const int n_items = P.first_block[P.S];
 
     // ---- carve shared memory: [ring of stages, 1024-byte aligned][T][column taps of every job][row table] ----
@@ -319,7 +356,7 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
             TC_TR_ADD(4);
             for (int ji = 0; ji < w.n_jobs; ++ji, ++jg) {
                 const GaborJob job = sc.jobs[ji];
-                const int h = job.h, buf = jg & 1;
+                const int h = Q.job_h[w.s * TC_CTAP_JOBS + ji], buf = jg & 1;
                 const float *w_col = stage_taps_window<GB_RC>(tap_col + (size_t)ji * P.tap_slot, job.col_im, h);
                 const int nblk_col = (2 * h + GB_RC + GB_RC - 1) / GB_RC;
                 if (h != cur_h || w.y0 != cur_y0) {
@@ -359,10 +396,12 @@ gabor_tc_kernel(const __grid_constant__ TcParams Q, const __grid_constant__ CUte
                 float *f0 = featb + (size_t)(d0 + job.out0) * P.feat_plane_stride;
                 float *f1 = job.out1 >= 0 ? featb + (size_t)(d0 + job.out1) * P.feat_plane_stride : nullptr;
                 const int *rt = rowtab;
-                const bool cx = job.row_im >= 0, ct = job.col_im >= 0;
+                const int kind = Q.job_kind[w.s * TC_CTAP_JOBS + ji];
+                const bool cx = kind & 1, ct = kind & 2;
                 long long *st0 = STATS ? P.stats + ((size_t)w.b * D + d0 + job.out0) * GB_STAT_SLOTS : nullptr;
                 long long *st1 = STATS && job.out1 >= 0 ? P.stats + ((size_t)w.b * D + d0 + job.out1) * GB_STAT_SLOTS : nullptr;
-                col_pass_dispatch<STATS>(cx, ct, P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW, st0, st1, h);
+                const ConstTaps ctaps{Q.ctap_w0[w.s * TC_CTAP_JOBS + ji]};
+                col_pass_dispatch<STATS>(cx, ct, P, T, rt, w_col, nblk_col, w.y0, w.th, w.x0, f0, f1, TC_COLW, st0, st1, h, ctaps);
                 TC_TR_ADD(3);
                 named_bar_sync(1, TC_COLT);                                          // T may be overwritten
                 TC_TR_ADD(5);
@@ -429,6 +468,8 @@ double bf16_value(uint16_t h)
 
 struct GaborTcPlan {
     TcParams q;
+    std::vector<float2> ctaps;                 // complex column taps as c_ctaps holds them
+    unsigned long long ctaps_id = 0;           // hash of ctaps: plans with the same bank share the upload
     size_t smem = 0;
     int kt = 0, table_rows = 0;                // B-operand table: [table_rows][kt] bf16
     __nv_bfloat16 *d_table = nullptr;
@@ -519,6 +560,35 @@ GaborTcPlan *gabor_tc_plan_new(const GaborBankHost &bank, int H, int W, int C, i
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bank.scales[a].hmax > bank.scales[b].hmax; });
     for (int i = 0; i < bank.S; ++i) p.order[i] = order[i];
 
+    // ---- complex column taps for the constant table (ConstTaps); a bank that does not fit runs on the FP32 kernel ----
+    {
+        int used = 0;
+        tp->ctaps.assign(TC_CTAP_CAP, make_float2(0.f, 0.f));
+        for (int s = 0; s < bank.S; ++s) {
+            const GaborScale &sc = bank.scales[s];
+            const int slot = 2 * sc.hmax + 1 + 2 * GB_TAP_PAD + 2 + 4;
+            if (sc.n_jobs > TC_CTAP_JOBS || used + sc.n_jobs * slot > TC_CTAP_CAP) { delete tp; return nullptr; }
+            tp->q.ctap_base[s] = used; tp->q.ctap_slot[s] = slot;
+            for (int ji = 0; ji < sc.n_jobs; ++ji) {
+                const GaborJob &job = sc.jobs[ji];
+                tp->q.ctap_w0[s * TC_CTAP_JOBS + ji] = -1;
+                tp->q.job_h[s * TC_CTAP_JOBS + ji] = job.h;
+                tp->q.job_kind[s * TC_CTAP_JOBS + ji] = (job.row_im >= 0 ? 1 : 0) | (job.col_im >= 0 ? 2 : 0);
+                if (job.col_im < 0) continue;
+                const int ntap = 2 * job.h + 1 + 2 * GB_TAP_PAD;
+                float2 *dst = tp->ctaps.data() + used + ji * slot;
+                for (int i = 1; i <= ntap; ++i) dst[i] = make_float2(bank.taps[job.col_re + i - 1], bank.taps[job.col_im + i - 1]);
+                tp->q.ctap_w0[s * TC_CTAP_JOBS + ji] = used + ji * slot + GB_TAP_PAD + 2 * job.h + 2 - GB_RC;
+            }
+            used += sc.n_jobs * slot;
+        }
+        tp->ctaps.resize(used);
+        unsigned long long hsh = 1469598103934665603ull;   // FNV-1a over the table
+        const unsigned char *bytes = reinterpret_cast<const unsigned char *>(tp->ctaps.data());
+        for (size_t i = 0; i < tp->ctaps.size() * sizeof(float2); ++i) hsh = (hsh ^ bytes[i]) * 1099511628211ull;
+        tp->ctaps_id = hsh | 1ull;
+    }
+
     // ---- B-operand table: per (scale, job, split term) a [64 n][kt] bf16 matrix, n = 2 c + (re|im) ----
     int kmax = 0, rows = 0;
     for (int s = 0; s < bank.S; ++s) {
@@ -599,6 +669,19 @@ int gabor_tc_launch(GaborTcPlan &tp, const void *d_planes16, float *d_feat, cons
         GCIS_CUDA_TRY(cudaFuncSetAttribute(gabor_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem));
         GCIS_CUDA_TRY(cudaFuncSetAttribute(gabor_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem));
         attr_smem = tp.smem;
+    }
+    // constant table: one bank per device at a time.  A change of bank waits for the kernels that still read the old one;
+    // the lock is held until this launch is in its stream, so that no other host thread swaps the table in between.
+    static std::mutex mu;
+    static unsigned long long owner[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (owner[dev & 63] != tp.ctaps_id) {
+        if (owner[dev & 63]) GCIS_CUDA_TRY(cudaDeviceSynchronize());
+        owner[dev & 63] = 0;
+        GCIS_CUDA_TRY(cudaMemcpyToSymbol(c_ctaps, tp.ctaps.data(), tp.ctaps.size() * sizeof(float2)));
+        owner[dev & 63] = tp.ctaps_id;
     }
     static const int n_sm = [] {
         int dev = 0, n = 0;

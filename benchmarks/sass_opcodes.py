@@ -14,7 +14,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 PATTERNS = [("UTC*MMA (tcgen05.mma)", r"\bUTC[A-Z]*MMA"), ("LDTM (tcgen05.ld)", r"\bLDTM"), ("STTM", r"\bSTTM"),
             ("UTCBAR (tcgen05.commit)", r"\bUTCBAR"), ("UTMALDG (TMA tensor load)", r"\bUTMALDG"), ("UBLKCP (bulk copy)", r"\bUBLKCP"),
-            ("SYNCS (mbarrier)", r"\bSYNCS"), ("FFMA2", r"\bFFMA2"), ("FFMA", r"\bFFMA\b"), ("IMMA (mma.sync s8)", r"\bIMMA"),
+            ("SYNCS (mbarrier)", r"\bSYNCS"), ("FFMA2", r"\bFFMA2"), ("FFMA2 with a uniform-register pair operand", r"\bFFMA2\b.*\bUR\d+"),
+            ("LDCU (uniform constant load)", r"\bLDCU"), ("FFMA", r"\bFFMA\b"), ("IMMA (mma.sync s8)", r"\bIMMA"),
             ("HMMA (mma.sync f16)", r"\bHMMA"), ("ACQBULK/PDL", r"\bACQBULK|\bPREEXIT"), ("total instructions", r"^\s+/\*[0-9a-f]{4,}\*/")]
 
 

@@ -701,5 +701,17 @@ def main():
     return run_gpu(args)
 
 
+def _keep_stdout_for_the_json_line():
+    """Native libraries write to file descriptor 1 (NCCL prints its version there): point it at stderr and keep the
+    real stdout for Python's prints, i.e. the one JSON line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    _keep_stdout_for_the_json_line()
+    rc = main()
+    sys.stdout.flush()
+    sys.exit(rc)

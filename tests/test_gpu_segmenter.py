@@ -201,3 +201,36 @@ def test_segmenter_slot_callable():
     m = metrics(img, labels, list(synth_ground_truths(3, 80, 100, 3)))
     m.set_metrics()
     assert 0.0 <= m.recall <= 1.0 and int(m.n_segments) <= 5
+
+
+def test_two_banks_alternate_on_one_device():
+    """The tensor-core filter bank keeps its complex column taps in constant memory, one bank per device at a time
+    (csrc/gabor_tc.cu: c_ctaps): two live plans with different banks must each see their own taps when they alternate."""
+    torch = _torch()
+    from gabor_color_image_segmentation_b200 import GaborBank, Plan
+    from oracle import oracle as orc
+    H, W = 64, 70
+    img = np.random.default_rng(11).integers(0, 256, (1, H, W, 3)).astype(np.uint8)
+    d_img = torch.from_numpy(img).cuda()
+    plans = [Plan(H, W, max_batch=1, bank=GaborBank.default(*a), k=4, iters=2, max_gt=0) for a in ((2, 6), (3, 4))]
+    assert all(p.uses_tensor_cores for p in plans)
+    first = [p.gabor_features(d_img).cpu().numpy() for p in plans]
+    for a, f in zip(((2, 6), (3, 4)), first):
+        _check_features(f[0], orc.gabor_features(img[0], orc.Bank.default(*a), "rgb"))
+    for _ in range(3):
+        for p, f in zip(plans, first):
+            assert np.array_equal(p.gabor_features(d_img).cpu().numpy(), f)
+
+
+def test_bank_beyond_the_constant_table_runs_on_the_fp32_kernel():
+    """More jobs per scale than the constant tap table covers (16 orientations = 9 jobs > 8): the plan falls back to the
+    FP32-pipe kernel and the features are the same function."""
+    torch = _torch()
+    from gabor_color_image_segmentation_b200 import GaborBank, Plan
+    from oracle import oracle as orc
+    H, W = 40, 48
+    img = np.random.default_rng(12).integers(0, 256, (1, H, W, 3)).astype(np.uint8)
+    plan = Plan(H, W, max_batch=1, bank=GaborBank.default(1, 16), k=4, iters=2, max_gt=0)
+    assert not plan.uses_tensor_cores
+    feat = plan.gabor_features(torch.from_numpy(img).cuda()).cpu().numpy()
+    _check_features(feat[0], orc.gabor_features(img[0], orc.Bank.default(1, 16), "rgb"))

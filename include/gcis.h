@@ -129,7 +129,8 @@ GCIS_API int64_t gcis_plan_workspace_bytes(const gcis_plan *plan);
 /* images per kernel launch when a batch of B images runs through the plan (the batch is cut into equal groups) */
 GCIS_API int32_t gcis_plan_launch_group(const gcis_plan *plan, int32_t B);
 /* 1 when the filter bank's row pass runs on the tcgen05 tensor cores (rgb planes, exact in bf16), 0 when both
- * passes run on the FP32 pipe (opponent / Lab planes, or GCIS_GABOR_TC=0) */
+ * passes run on the FP32 pipe (opponent / Lab planes, GCIS_GABOR_TC=0, or a bank beyond the kernel's constant tap
+ * table: more than 8 orientation jobs per scale or more than 6144 complex column taps) */
 GCIS_API int32_t gcis_plan_uses_tensor_cores(const gcis_plan *plan);
 
 /* ---- segmenter slot (script.py:30), device pointers ----

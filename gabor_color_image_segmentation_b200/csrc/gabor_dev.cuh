@@ -95,8 +95,8 @@ template <int N> struct IntC { static constexpr int value = N; };
 
 // Tap source of sweep(): half(m, c, r) delivers the R new taps of block m (complex pairs in c, real taps in r).
 // SmemTaps reads the window stage_taps() laid out in shared memory (warp-uniform 128-bit loads into ordinary registers);
-// a kernel may pass a source of its own (gabor_tc.cu: the kernel's parameter space, so the taps live in UNIFORM registers
-// and the packed FMA reads only its accumulator pair and one scalar from the register file).
+// a kernel may pass a source of its own (gabor_tc.cu: a constant-memory table read tap by tap (DIRECT), so that the taps
+// live in UNIFORM registers and the packed FMA reads only its accumulator pair and one scalar from the register file).
 struct SmemTaps {
     static constexpr bool DIRECT = false;   // the taps are held in registers half a window at a time (half())
     const float *w0;   // window of block 0; the window moves down by R taps per block
